@@ -1,0 +1,121 @@
+/*
+ * fno_sm100.h -- C ABI of libfno_sm100.so: the B200 (sm_100a) implementation of the FNO
+ * spectral-convolution training path of mehrdadmmz/SciML-PDE.
+ *
+ * The reference has no FFI: its seam is the Python nn.Module protocol, and all arithmetic is
+ * delegated to PyTorch library calls.  Each entry point below states the reference call site(s)
+ * (path:line under /root/reference/pdebench/models) whose work it replaces.  The host-side
+ * mirror of the reference modules (sciml-pde_b200/fno_b200) binds exactly these symbols through
+ * ctypes; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory (the torch caching allocator
+ *     owns all bytes); the library owns only immutable twiddle tables inside a plan;
+ *   - real tensors are float32, complex tensors are interleaved (re, im) float32 pairs
+ *     (= torch.complex64 storage); all tensors are dense/contiguous in the stated layout;
+ *   - every compute call is asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronises, never allocates: safe under CUDA-graph capture and from PyTorch's autograd
+ *     thread; plans may be shared between threads once created;
+ *   - return value: 0 = ok, < 0 = error (FNO_E_*); fno_last_error() gives the thread-local text.
+ *     There is no CPU fallback: on a device that is not sm_100 every call fails with FNO_E_ARCH.
+ *
+ * Spectrum layout ("retained modes"): for a 2-D plane [H, W] with modes (m1, m2) the kept
+ * spectrum is X[2*m1, m2]: rows 0..m1-1 are k1 = 0..m1-1 (reference slice `:m1`, weights1), rows
+ * m1..2*m1-1 are k1 = H-m1..H-1 (slice `-m1:`, weights2); columns are k2 = 0..m2-1 of the
+ * half spectrum.  3-D: X[2*m1, 2*m2, m3], corner (r1 >= m1) + 2*(r2 >= m2) <-> weights1..4
+ * (fno/fno.py:274-285).
+ */
+#ifndef FNO_SM100_H
+#define FNO_SM100_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FNO_OK 0
+#define FNO_E_ARG (-1)     /* bad shape / null pointer / unsupported size */
+#define FNO_E_CUDA (-2)    /* CUDA runtime error (text in fno_last_error) */
+#define FNO_E_ARCH (-3)    /* device is not sm_100 */
+#define FNO_E_NOMEM (-4)   /* plan table allocation failed */
+
+typedef struct fno_plan fno_plan;
+typedef void* fno_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int fno_version(void);                         /* 100 * major + minor */
+int fno_sm_arch(void);                         /* 100: the only architecture compiled in */
+const char* fno_last_error(void);              /* thread-local, never NULL */
+unsigned long long fno_launch_count(void);     /* kernels launched by this library so far */
+void fno_shutdown(void);                       /* destroys every live plan */
+
+/* ---- plans: immutable twiddle tables for one transform geometry ---------------------------- */
+/* 2-D plane [H, W], modes (m1, m2); requires 2*m1 <= H, m2 <= W/2+1, m1 <= 32.              */
+int fno_plan2d_create(int device, int H, int W, int m1, int m2, fno_plan** out);
+/* 3-D volume [D1, D2, D3], modes (m1, m2, m3); 2*m1 <= D1, 2*m2 <= D2, m3 <= D3/2+1.        */
+int fno_plan3d_create(int device, int D1, int D2, int D3, int m1, int m2, int m3, fno_plan** out);
+int fno_plan_destroy(fno_plan* plan);
+/* bytes of scratch a 3-D transform call needs for `planes` volumes (0 for a 2-D plan).       */
+size_t fno_plan_workspace_bytes(const fno_plan* plan, long planes);
+
+/* ---- K1: pruned real-to-complex forward transform ------------------------------------------ */
+/* Replaces torch.fft.rfft2(x)[..., kept modes] (fno/fno.py:73, slices :84-89) and, with
+ * cmode = 1 / scale = 1/(H*W), the autograd backward of torch.fft.irfft2 (fno/fno.py:92).
+ *   x      [planes, H, W] f32
+ *   preact optional [planes, H, W] f32: if given the transform input is x * gelu'(preact)
+ *          (backward of F.gelu, fno/fno.py:164) and, if ds_out is given, that product is stored
+ *   X      [planes, 2*m1, m2] complex64 out, multiplied by scale (and c_k2 if cmode = 1)      */
+int fno_sc2d_fwd_transform(const fno_plan* plan, const float* x, const float* preact,
+                           float* ds_out, float* X, long planes, int cmode, float scale,
+                           fno_stream_t stream);
+/* 3-D twin (torch.fft.rfftn, fno/fno.py:262): x [planes, D1, D2, D3] -> X [planes, 2m1, 2m2, m3];
+ * work: fno_plan_workspace_bytes(plan, planes) bytes of scratch.                               */
+int fno_sc3d_fwd_transform(const fno_plan* plan, const float* x, const float* preact,
+                           float* ds_out, float* X, void* work, long planes, int cmode,
+                           float scale, fno_stream_t stream);
+
+/* ---- K2: per-mode complex channel mixing ---------------------------------------------------- */
+/* compl_mul2d / compl_mul3d (fno/fno.py:66-68, :255-257) for all corners in one launch:
+ *   Y[b,o,k] = sum_i X[b,i,k] * Wcorner(k)[i,o,k]
+ *   X [B, Ci, M] c64, Y [B, Co, M] c64, M = modes of the plan's retained spectrum;
+ *   w[0..ncorners) device pointers to the corner parameters, each [Ci, Co, m1, m2(, m3)] c64
+ *   in the reference's own state_dict layout (2 corners for a 2-D plan, 4 for a 3-D plan).     */
+int fno_mix_fwd(const fno_plan* plan, const float* X, const float* const* w, float* Y, int B,
+                int Ci, int Co, fno_stream_t stream);
+/* autograd backward of the einsum: gX[b,i,k] = sum_o gY[b,o,k] conj(W[i,o,k]);
+ * gW[i,o,k] = sum_b conj(X[b,i,k]) gY[b,o,k] written per corner into gw[0..ncorners).
+ * gX or gw may be NULL to skip that half.                                                      */
+int fno_mix_bwd(const fno_plan* plan, const float* X, const float* gY, const float* const* w,
+                float* gX, float* const* gw, int B, int Ci, int Co, fno_stream_t stream);
+
+/* ---- K3: zero-padding inverse transform with fused epilogue --------------------------------- */
+/* Replaces torch.zeros + slice-assign + torch.fft.irfft2 (fno/fno.py:76-92) and, when `addend`
+ * / `apply_gelu` are used, also `x1 + x2` and F.gelu (fno/fno.py:163-164).
+ *   Y       [planes, 2*m1, m2] c64
+ *   addend  optional [planes, H, W] f32 added to the transform (may alias `out`)
+ *   s_out   optional [planes, H, W] f32: receives the pre-activation (transform + addend)
+ *   out     [planes, H, W] f32: gelu(pre-activation) if apply_gelu else the pre-activation
+ *   cmode = 1, scale = 1/(H*W): irfft2 semantics; cmode = 0, scale = 1: adjoint of K1.        */
+int fno_sc2d_inv_transform(const fno_plan* plan, const float* Y, const float* addend,
+                           float* s_out, float* out, long planes, int cmode, float scale,
+                           int apply_gelu, fno_stream_t stream);
+int fno_sc3d_inv_transform(const fno_plan* plan, const float* Y, const float* addend,
+                           float* s_out, float* out, void* work, long planes, int cmode,
+                           float scale, int apply_gelu, fno_stream_t stream);
+
+/* ---- 1x1-conv bypass (nn.Conv2d/3d(width, width, 1); fno/fno.py:131-134,162) ----------------- */
+/* out[b,o,p] = sum_i W[o,i] in[b,i,p] (+ bias[o]);  transpose != 0: out[b,i,p] = sum_o W[o,i] in[b,o,p]
+ *   in [B, Cin, N], out [B, Cout, N], W [Co, Ci] (the conv weight viewed 2-D), N = pixels/sample */
+int fno_pointwise_fwd(const float* in, const float* W, const float* bias, float* out, int B,
+                      int Co, int Ci, long N, int transpose, fno_stream_t stream);
+/* gW[o,i] = sum_{b,p} ds[b,o,p] a[b,i,p];  gb[o] = sum_{b,p} ds[b,o,p].
+ * work: fno_pointwise_wgrad_workspace_bytes(B, C, C, N) bytes of scratch.                       */
+size_t fno_pointwise_wgrad_workspace_bytes(int B, int Co, int Ci, long N);
+int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B,
+                        int Co, int Ci, long N, fno_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FNO_SM100_H */

@@ -1,0 +1,65 @@
+// Shared declarations for libfno_sm100.so (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/fno_sm100.h"
+
+namespace fno {
+
+// ---- plan ------------------------------------------------------------------------------------
+// Immutable per-geometry tables, all in device memory.
+//   twH  [NP][JP]   folded row twiddles for the strided axis of a 2-D plane, NP = H/2+1:
+//                   cols 0..M1T      cos(2 pi j t / H)
+//                   cols M1T+1..2M1T sin(2 pi j t / H), j = 1..M1T   (0 beyond m1)
+//   twW  [2][m2][WP] cos / sin of 2 pi k2 w / W, WP = roundup(W, 4), zero padded
+//   twX  [D1][2*m1][2]  (3-D only) cos / sin of 2 pi k1 d / D1 for the kept signed rows
+struct Plan {
+  int nd;            // 2 or 3
+  int device;
+  int D1;            // 3-D only: outer (strided) axis handled by the axis kernels
+  int H, W;          // 2-D plane extents (3-D: D2, D3)
+  int m1x;           // 3-D only: modes along D1
+  int m1, m2;        // modes of the 2-D plane transform (3-D: m2, m3)
+  int M1T;           // m1 rounded up to an instantiated template size
+  int NP, JP, WP;
+  float* twH;
+  float* twW;
+  float* twX;
+  int G_fwd, G_inv;  // planes per CTA
+};
+
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- kernel launchers (one per translation unit) -------------------------------------------
+int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_out, float* X,
+                 long planes, int cmode, float scale, cudaStream_t st);
+int launch_inv2d(const Plan* p, const float* Y, const float* addend, float* s_out, float* out,
+                 long planes, int cmode, float scale, int apply_gelu, cudaStream_t st);
+int setup_transform2d_attrs(const Plan* p);
+int launch_axis_fwd(const Plan* p, const float* S, float* X, long planes, long Q, cudaStream_t st);
+int launch_axis_inv(const Plan* p, const float* Y, float* Z, long planes, long Q, cudaStream_t st);
+int launch_mix_fwd(const Plan* p, const float* X, const float* const* w, float* Y, int B, int Ci,
+                   int Co, cudaStream_t st);
+int launch_mix_bwd_data(const Plan* p, const float* gY, const float* const* w, float* gX, int B,
+                        int Ci, int Co, cudaStream_t st);
+int launch_mix_bwd_weight(const Plan* p, const float* X, const float* gY, float* const* gw, int B,
+                          int Ci, int Co, cudaStream_t st);
+
+// ---- device helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_exact(float s) {
+  return 0.5f * s * (1.0f + erff(s * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float gelu_exact_grad(float s) {
+  const float cdf = 0.5f * (1.0f + erff(s * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * s * s);
+  return fmaf(s, pdf, cdf);
+}
+
+}  // namespace fno

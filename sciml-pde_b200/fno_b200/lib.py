@@ -1,0 +1,312 @@
+"""ctypes binding of libfno_sm100.so (include/fno_sm100.h) for torch CUDA tensors.
+
+PyTorch is plumbing here: it owns device memory and streams.  Every function below passes raw
+device pointers plus the caller's *current* CUDA stream to the C ABI; nothing is computed in
+Python and there is no CPU / eager fallback -- a missing library or a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / "libfno_sm100.so"
+_lib = None
+_lib_lock = threading.Lock()
+
+c_float_p = C.POINTER(C.c_float)
+
+
+class FnoError(RuntimeError):
+    pass
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load():
+    """Loads the shared library (once).  Raises FnoError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not _LIB_PATH.exists():
+            raise FnoError(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  There is no CPU fallback for the FNO spectral-convolution path."
+            )
+        lib = C.CDLL(str(_LIB_PATH))
+        vp, i, l, f = C.c_void_p, C.c_int, C.c_long, C.c_float
+        vpp = C.POINTER(C.c_void_p)
+        sig = {
+            "fno_version": (i, []),
+            "fno_sm_arch": (i, []),
+            "fno_last_error": (C.c_char_p, []),
+            "fno_launch_count": (C.c_ulonglong, []),
+            "fno_shutdown": (None, []),
+            "fno_plan2d_create": (i, [i, i, i, i, i, vpp]),
+            "fno_plan3d_create": (i, [i, i, i, i, i, i, i, vpp]),
+            "fno_plan_destroy": (i, [vp]),
+            "fno_plan_workspace_bytes": (C.c_size_t, [vp, l]),
+            "fno_sc2d_fwd_transform": (i, [vp, vp, vp, vp, vp, l, i, f, vp]),
+            "fno_sc3d_fwd_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, vp]),
+            "fno_mix_fwd": (i, [vp, vp, vpp, vp, i, i, i, vp]),
+            "fno_mix_bwd": (i, [vp, vp, vp, vpp, vp, vpp, i, i, i, vp]),
+            "fno_sc2d_inv_transform": (i, [vp, vp, vp, vp, vp, l, i, f, i, vp]),
+            "fno_sc3d_inv_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, i, vp]),
+            "fno_pointwise_fwd": (i, [vp, vp, vp, vp, i, i, i, l, i, vp]),
+            "fno_pointwise_wgrad_workspace_bytes": (C.c_size_t, [i, i, i, l]),
+            "fno_pointwise_wgrad": (i, [vp, vp, vp, vp, vp, i, i, i, l, vp]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+EXPORTED_SYMBOLS = (
+    "fno_version", "fno_sm_arch", "fno_last_error", "fno_launch_count", "fno_shutdown",
+    "fno_plan2d_create", "fno_plan3d_create", "fno_plan_destroy", "fno_plan_workspace_bytes",
+    "fno_sc2d_fwd_transform", "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
+    "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
+    "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
+)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().fno_last_error().decode("utf-8", "replace")
+        raise FnoError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count() -> int:
+    return int(load().fno_launch_count())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require(t: torch.Tensor, dtype, name: str):
+    if not t.is_cuda:
+        raise FnoError(f"{name} must be a CUDA tensor (libfno_sm100 has no CPU path); got device {t.device}")
+    if t.dtype != dtype:
+        raise FnoError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise FnoError(f"{name} must be contiguous")
+
+
+# ---------------------------------------------------------------------------------------------
+# plans (cached per device / geometry; immutable, thread-safe once created)
+# ---------------------------------------------------------------------------------------------
+class Plan:
+    def __init__(self, handle: int, device: int, spatial: Sequence[int], modes: Sequence[int]):
+        self.handle = handle
+        self.device = device
+        self.spatial = tuple(spatial)
+        self.modes = tuple(modes)
+        self.nd = len(spatial)
+
+    @property
+    def spec_shape(self):
+        """Retained-spectrum extents: (2*m1, m2) or (2*m1, 2*m2, m3)."""
+        return tuple(2 * m for m in self.modes[:-1]) + (self.modes[-1],)
+
+    @property
+    def num_modes(self) -> int:
+        n = 1
+        for s in self.spec_shape:
+            n *= s
+        return n
+
+    @property
+    def npix(self) -> int:
+        n = 1
+        for s in self.spatial:
+            n *= s
+        return n
+
+    def workspace(self, planes: int, device) -> Optional[torch.Tensor]:
+        if self.nd == 2:
+            return None
+        nbytes = load().fno_plan_workspace_bytes(self.handle, planes)
+        return torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+
+
+_plans: dict = {}
+_plans_lock = threading.Lock()
+
+
+def get_plan(device: torch.device, spatial: Sequence[int], modes: Sequence[int]) -> Plan:
+    if device.type != "cuda":
+        raise FnoError(f"the FNO spectral path runs on CUDA (sm_100a) only, got device {device}")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (idx, tuple(int(s) for s in spatial), tuple(int(m) for m in modes))
+    plan = _plans.get(key)
+    if plan is not None:
+        return plan
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is not None:
+            return plan
+        lib = load()
+        h = C.c_void_p()
+        if len(spatial) == 2:
+            rc = lib.fno_plan2d_create(idx, int(spatial[0]), int(spatial[1]), int(modes[0]), int(modes[1]), C.byref(h))
+        elif len(spatial) == 3:
+            rc = lib.fno_plan3d_create(idx, *[int(s) for s in spatial], *[int(m) for m in modes], C.byref(h))
+        else:
+            raise FnoError("only 2-D and 3-D spectral convolutions exist in the reference")
+        _check(rc, "fno_plan_create")
+        plan = Plan(h.value, idx, spatial, modes)
+        _plans[key] = plan
+    return plan
+
+
+def shutdown():
+    with _plans_lock:
+        _plans.clear()
+        if _lib is not None:
+            _lib.fno_shutdown()
+
+
+# ---------------------------------------------------------------------------------------------
+# thin call wrappers (shape bookkeeping only)
+# ---------------------------------------------------------------------------------------------
+def fwd_transform(plan: Plan, x: torch.Tensor, *, preact: Optional[torch.Tensor] = None,
+                  ds_out: Optional[torch.Tensor] = None, cmode: int = 0, scale: float = 1.0) -> torch.Tensor:
+    """x [B, C, *spatial] f32 -> retained spectrum [B, C, *spec_shape] complex64."""
+    _require(x, torch.float32, "x")
+    if tuple(x.shape[-plan.nd:]) != plan.spatial:
+        raise FnoError(f"x spatial dims {tuple(x.shape[-plan.nd:])} do not match plan {plan.spatial}")
+    planes = x.numel() // plan.npix
+    if preact is not None:
+        _require(preact, torch.float32, "preact")
+    if ds_out is not None:
+        _require(ds_out, torch.float32, "ds_out")
+    X = torch.empty(tuple(x.shape[:-plan.nd]) + plan.spec_shape, dtype=torch.complex64, device=x.device)
+    lib = load()
+    if plan.nd == 2:
+        rc = lib.fno_sc2d_fwd_transform(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(), planes,
+                                        cmode, scale, _stream())
+    else:
+        work = plan.workspace(planes, x.device)
+        rc = lib.fno_sc3d_fwd_transform(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(),
+                                        work.data_ptr(), planes, cmode, scale, _stream())
+    _check(rc, "fno_fwd_transform")
+    return X
+
+
+def inv_transform(plan: Plan, Y: torch.Tensor, *, addend: Optional[torch.Tensor] = None,
+                  s_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, cmode: int = 1,
+                  scale: Optional[float] = None, apply_gelu: bool = False) -> torch.Tensor:
+    """Y [B, C, *spec_shape] complex64 -> [B, C, *spatial] f32 (+addend, optional GELU)."""
+    _require(Y, torch.complex64, "Y")
+    if tuple(Y.shape[-plan.nd:]) != plan.spec_shape:
+        raise FnoError(f"Y mode dims {tuple(Y.shape[-plan.nd:])} do not match plan {plan.spec_shape}")
+    lead = tuple(Y.shape[:-plan.nd])
+    planes = Y.numel() // plan.num_modes
+    if scale is None:
+        scale = 1.0 / plan.npix
+    if out is None:
+        out = torch.empty(lead + plan.spatial, dtype=torch.float32, device=Y.device)
+    _require(out, torch.float32, "out")
+    if addend is not None:
+        _require(addend, torch.float32, "addend")
+    if s_out is not None:
+        _require(s_out, torch.float32, "s_out")
+    lib = load()
+    if plan.nd == 2:
+        rc = lib.fno_sc2d_inv_transform(plan.handle, Y.data_ptr(), _ptr(addend), _ptr(s_out), out.data_ptr(), planes,
+                                        cmode, scale, int(apply_gelu), _stream())
+    else:
+        work = plan.workspace(planes, Y.device)
+        rc = lib.fno_sc3d_inv_transform(plan.handle, Y.data_ptr(), _ptr(addend), _ptr(s_out), out.data_ptr(),
+                                        work.data_ptr(), planes, cmode, scale, int(apply_gelu), _stream())
+    _check(rc, "fno_inv_transform")
+    return out
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    arr = (C.c_void_p * len(tensors))()
+    for k, t in enumerate(tensors):
+        arr[k] = t.data_ptr()
+    return arr
+
+
+def mix_fwd(plan: Plan, X: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    _require(X, torch.complex64, "X")
+    B, Ci = X.shape[0], X.shape[1]
+    Co = weights[0].shape[1]
+    for k, w in enumerate(weights):
+        _require(w, torch.complex64, f"weights{k + 1}")
+        if tuple(w.shape) != (Ci, Co) + plan.modes:
+            raise FnoError(f"weights{k + 1} shape {tuple(w.shape)} != {(Ci, Co) + plan.modes}")
+    Y = torch.empty((B, Co) + plan.spec_shape, dtype=torch.complex64, device=X.device)
+    rc = load().fno_mix_fwd(plan.handle, X.data_ptr(), _ptr_array(weights), Y.data_ptr(), B, Ci, Co, _stream())
+    _check(rc, "fno_mix_fwd")
+    return Y
+
+
+def mix_bwd(plan: Plan, X: Optional[torch.Tensor], gY: torch.Tensor, weights: Sequence[torch.Tensor], *,
+            need_gx: bool = True, need_gw: bool = True):
+    _require(gY, torch.complex64, "gY")
+    B, Co = gY.shape[0], gY.shape[1]
+    Ci = weights[0].shape[0]
+    gX = torch.empty((B, Ci) + plan.spec_shape, dtype=torch.complex64, device=gY.device) if need_gx else None
+    gws = [torch.empty_like(w) for w in weights] if need_gw else None
+    if need_gw:
+        _require(X, torch.complex64, "X")
+    rc = load().fno_mix_bwd(plan.handle, _ptr(X), gY.data_ptr(), _ptr_array(weights), _ptr(gX),
+                            _ptr_array(gws) if need_gw else None, B, Ci, Co, _stream())
+    _check(rc, "fno_mix_bwd")
+    return gX, gws
+
+
+def pointwise_fwd(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transpose: bool = False,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """1x1 conv on channel-first [B, C, *spatial]; weight is the conv weight [Co, Ci, 1, 1(, 1)]."""
+    _require(a, torch.float32, "a")
+    _require(weight, torch.float32, "weight")
+    Co, Ci = weight.shape[0], weight.shape[1]
+    B = a.shape[0]
+    N = a.numel() // (B * a.shape[1])
+    cin, cout = (Co, Ci) if transpose else (Ci, Co)
+    if a.shape[1] != cin:
+        raise FnoError(f"pointwise: input has {a.shape[1]} channels, expected {cin}")
+    if out is None:
+        out = torch.empty((B, cout) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
+    if bias is not None:
+        _require(bias, torch.float32, "bias")
+    rc = load().fno_pointwise_fwd(a.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), B, Co, Ci, N,
+                                  int(transpose), _stream())
+    _check(rc, "fno_pointwise_fwd")
+    return out
+
+
+def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True):
+    _require(ds, torch.float32, "ds")
+    _require(a, torch.float32, "a")
+    B, Co, Ci = ds.shape[0], ds.shape[1], a.shape[1]
+    N = ds.numel() // (B * Co)
+    lib = load()
+    nbytes = lib.fno_pointwise_wgrad_workspace_bytes(B, Co, Ci, N)
+    work = torch.empty(nbytes // 4, dtype=torch.float32, device=ds.device)
+    gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=ds.device)
+    gb = torch.empty(Co, dtype=torch.float32, device=ds.device) if need_bias else None
+    rc = lib.fno_pointwise_wgrad(ds.data_ptr(), a.data_ptr(), gw.data_ptr(), _ptr(gb), work.data_ptr(), B, Co, Ci, N,
+                                 _stream())
+    _check(rc, "fno_pointwise_wgrad")
+    return gw, gb

@@ -1,0 +1,119 @@
+"""torch.autograd glue for the sm_100a kernels: the spectral convolution operator and the fused
+Fourier layer.  Each Function's forward/backward is a fixed sequence of C-ABI launches on the
+current stream (no host sync, no Python arithmetic on tensor values), so a whole trunk can be
+captured in a CUDA graph.
+
+Math (checked by tests against oracle/dft_oracle.py):
+    forward   X = K1(x);  Y = K2(X, W);  y = K3(Y)
+    backward  gY = (c/N) K1(g);  gX, gW = K2'(X, gY, W);  gx = K3(gX; c = 1, scale = 1)
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+from . import lib
+
+
+def _plan_for(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> lib.Plan:
+    modes = tuple(weights[0].shape[2:])
+    nd = len(modes)
+    if nd not in (2, 3) or len(weights) != (2 if nd == 2 else 4):
+        raise lib.FnoError("expected 2 corner weights [Ci,Co,m1,m2] (2-D) or 4 [Ci,Co,m1,m2,m3] (3-D)")
+    if x.dim() != nd + 2:
+        raise lib.FnoError(f"input must be [B, C, {'H, W' if nd == 2 else 'D1, D2, D3'}], got {tuple(x.shape)}")
+    return lib.get_plan(x.device, tuple(x.shape[-nd:]), modes)
+
+
+class SpectralConvFn(torch.autograd.Function):
+    """y = irfftn(scatter(einsum(rfftn(x)[corners], W)))  -- fno/fno.py:70-92, :259-288."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        x = x.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        plan = _plan_for(x, weights)
+        X = lib.fwd_transform(plan, x)
+        Y = lib.mix_fwd(plan, X, weights)
+        y = lib.inv_transform(plan, Y, cmode=1)
+        ctx.plan = plan
+        ctx.save_for_backward(X, *weights)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        X, *weights = ctx.saved_tensors
+        plan = ctx.plan
+        g = g.contiguous()
+        need_gx = ctx.needs_input_grad[0]
+        need_gw = any(ctx.needs_input_grad[1:])
+        gY = lib.fwd_transform(plan, g, cmode=1, scale=1.0 / plan.npix)
+        gX, gws = lib.mix_bwd(plan, X, gY, weights, need_gx=need_gx, need_gw=need_gw)
+        gx = lib.inv_transform(plan, gX, cmode=0, scale=1.0) if need_gx else None
+        if gws is None:
+            gws = [None] * len(weights)
+        return (gx, *gws)
+
+
+def spectral_conv(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    return SpectralConvFn.apply(x, *weights)
+
+
+class FourierLayerFn(torch.autograd.Function):
+    """a' = act(SpectralConv(a) + Conv1x1(a)),  act = exact GELU or identity (fno/fno.py:161-178).
+
+    Forward launches: bypass -> K1 -> K2 -> K3(+bypass, +GELU).  Saved for backward: a, the
+    pre-activation s (exact-erf GELU is not invertible from its output), the spectrum X.
+    Backward launches: K1(g * gelu'(s)) [stores dS] -> bypass weight/bias gradient ->
+    K2' -> bypass^T(dS) -> K3(gX) + bypass^T.
+    """
+
+    @staticmethod
+    def forward(ctx, a, wl, bl, apply_gelu, *weights):
+        a = a.contiguous()
+        weights = tuple(w.contiguous() for w in weights)
+        wl = wl.contiguous()
+        plan = _plan_for(a, weights)
+        training = any(ctx.needs_input_grad)
+        lin = lib.pointwise_fwd(a, wl, bl)
+        X = lib.fwd_transform(plan, a)
+        Y = lib.mix_fwd(plan, X, weights)
+        s = torch.empty_like(lin) if (training and apply_gelu) else None
+        out = lib.inv_transform(plan, Y, addend=lin, s_out=s, out=lin, cmode=1, apply_gelu=apply_gelu)
+        if training:
+            ctx.plan = plan
+            ctx.apply_gelu = bool(apply_gelu)
+            ctx.has_bias = bl is not None
+            ctx.save_for_backward(a, wl, X, s if s is not None else a.new_empty(0), *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, wl, X, s, *weights = ctx.saved_tensors
+        plan = ctx.plan
+        g = g.contiguous()
+        need_ga, need_wl, need_bl = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_gw = any(ctx.needs_input_grad[4:])
+        inv_n = 1.0 / plan.npix
+        if ctx.apply_gelu:
+            ds = torch.empty_like(g)
+            gY = lib.fwd_transform(plan, g, preact=s, ds_out=ds, cmode=1, scale=inv_n)
+        else:
+            ds = g
+            gY = lib.fwd_transform(plan, g, cmode=1, scale=inv_n)
+        gwl = gbl = None
+        if need_wl or (need_bl and ctx.has_bias):
+            gwl, gbl = lib.pointwise_wgrad(ds, a, wl.shape, need_bias=ctx.has_bias)
+        gX, gws = lib.mix_bwd(plan, X, gY, weights, need_gx=need_ga, need_gw=need_gw)
+        ga = None
+        if need_ga:
+            ga = lib.pointwise_fwd(ds, wl, None, transpose=True)
+            lib.inv_transform(plan, gX, addend=ga, out=ga, cmode=0, scale=1.0)
+        if gws is None:
+            gws = [None] * len(weights)
+        return (ga, gwl if need_wl else None, gbl if (need_bl and ctx.has_bias) else None, None, *gws)
+
+
+def fourier_layer(a, wl, bl, apply_gelu: bool, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    return FourierLayerFn.apply(a, wl, bl, apply_gelu, *weights)

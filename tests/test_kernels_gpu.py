@@ -1,0 +1,238 @@
+"""Kernel-level parity: every C-ABI entry point of libfno_sm100.so against the fp64 dense-DFT
+oracle (oracle/dft_oracle.py) on seeded inputs, plus the reference's own golden vectors.
+
+Tolerance (BASELINE.json north_star, fp32 mode): max-abs-err / max-abs-ref <= 1e-5.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dft_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fno_b200 import lib as L
+
+    L.load()
+    return L
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def cplx(rng, shape, scale=1.0):
+    return (scale * (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))).astype(np.complex64)
+
+
+PLANES_2D = [
+    # B, C, H, W, m1, m2
+    (2, 3, 10, 9, 3, 4),        # odd W
+    (1, 2, 7, 16, 2, 5),        # odd H
+    (2, 4, 12, 12, 6, 7),       # 2*m1 == H (corners touch), m2 == W/2+1 (Nyquist column)
+    (3, 5, 34, 34, 12, 12),
+    (2, 3, 130, 130, 12, 12),   # cfg 1 padded plane
+    (1, 2, 258, 258, 16, 16),   # cfg 3 padded plane
+    (1, 3, 64, 70, 12, 12),     # a 3-D slice of cfg 4
+    (5, 1, 20, 6, 1, 1),        # single mode
+    (1, 1, 66, 40, 32, 20),     # max supported modes1
+    (7, 3, 33, 31, 5, 9),       # ragged plane count vs planes-per-CTA
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", PLANES_2D)
+@pytest.mark.parametrize("cmode", [0, 1])
+def test_fwd_transform_2d(lib, B, C, H, W, m1, m2, cmode):
+    rng = np.random.default_rng(H * 1000 + W)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    scale = 1.0 if cmode == 0 else 1.0 / (H * W)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    X = lib.fwd_transform(plan, dev(x), cmode=cmode, scale=scale).cpu().numpy()
+    ref = O.fwd_transform(x, (m1, m2), cmode=cmode, scale=scale)
+    assert X.shape == ref.shape
+    assert O.rel_err(X, ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", PLANES_2D)
+@pytest.mark.parametrize("cmode", [0, 1])
+def test_inv_transform_2d(lib, B, C, H, W, m1, m2, cmode):
+    rng = np.random.default_rng(H * 1000 + W + 7)
+    Y = cplx(rng, (B, C, 2 * m1, m2))
+    scale = 1.0 if cmode == 0 else 1.0 / (H * W)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    y = lib.inv_transform(plan, dev(Y), cmode=cmode, scale=scale).cpu().numpy()
+    ref = O.inv_transform(Y, (H, W), cmode=cmode, scale=scale)
+    assert O.rel_err(y, ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", [(2, 3, 10, 9, 3, 4), (2, 3, 130, 130, 12, 12), (1, 2, 64, 70, 12, 12)])
+@pytest.mark.parametrize("gelu", [False, True])
+def test_inv_transform_fused_epilogue(lib, B, C, H, W, m1, m2, gelu):
+    rng = np.random.default_rng(11)
+    Y = cplx(rng, (B, C, 2 * m1, m2), scale=30.0)
+    add = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    addt = dev(add)
+    s_out = torch.empty_like(addt)
+    out = lib.inv_transform(plan, dev(Y), addend=addt, s_out=s_out, out=addt, cmode=1, apply_gelu=gelu)
+    assert out.data_ptr() == addt.data_ptr()  # in place over the addend
+    s_ref = O.inv_transform(Y, (H, W), cmode=1) + add
+    assert O.rel_err(s_out.cpu().numpy(), s_ref) < TOL
+    ref = O.gelu(s_ref) if gelu else s_ref
+    assert O.rel_err(out.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", [(2, 3, 10, 9, 3, 4), (2, 3, 130, 130, 12, 12)])
+def test_fwd_transform_gelu_grad_prologue(lib, B, C, H, W, m1, m2):
+    """bwd_pre: transform of g * gelu'(s), storing dS."""
+    rng = np.random.default_rng(12)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s = (2.0 * rng.standard_normal((B, C, H, W))).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    ds = torch.empty(B, C, H, W, device="cuda")
+    gY = lib.fwd_transform(plan, dev(g), preact=dev(s), ds_out=ds, cmode=1, scale=1.0 / (H * W))
+    ds_ref = g.astype(np.float64) * O.gelu_grad(s)
+    assert O.rel_err(ds.cpu().numpy(), ds_ref) < TOL
+    assert O.rel_err(gY.cpu().numpy(), O.fwd_transform(ds_ref, (m1, m2), cmode=1, scale=1.0 / (H * W))) < TOL
+
+
+VOLUMES_3D = [
+    # B, C, D1, D2, D3, m1, m2, m3
+    (2, 2, 8, 6, 10, 3, 2, 4),
+    (1, 3, 8, 8, 8, 4, 4, 5),     # touching corners on both full axes + Nyquist
+    (1, 2, 12, 10, 14, 4, 3, 4),
+    (1, 2, 64, 64, 70, 12, 12, 12),  # cfg 4 padded volume
+]
+
+
+@pytest.mark.parametrize("B,C,D1,D2,D3,m1,m2,m3", VOLUMES_3D)
+def test_transforms_3d(lib, B, C, D1, D2, D3, m1, m2, m3):
+    rng = np.random.default_rng(D1 + D2 + D3)
+    x = rng.standard_normal((B, C, D1, D2, D3)).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (D1, D2, D3), (m1, m2, m3))
+    X = lib.fwd_transform(plan, dev(x)).cpu().numpy()
+    assert O.rel_err(X, O.fwd_transform(x, (m1, m2, m3))) < TOL
+    n = D1 * D2 * D3
+    Xs = lib.fwd_transform(plan, dev(x), cmode=1, scale=1.0 / n).cpu().numpy()
+    assert O.rel_err(Xs, O.fwd_transform(x, (m1, m2, m3), cmode=1, scale=1.0 / n)) < TOL
+    Y = cplx(rng, (B, C, 2 * m1, 2 * m2, m3))
+    y = lib.inv_transform(plan, dev(Y), cmode=1).cpu().numpy()
+    assert O.rel_err(y, O.inv_transform(Y, (D1, D2, D3), cmode=1)) < TOL
+    y0 = lib.inv_transform(plan, dev(Y), cmode=0, scale=1.0).cpu().numpy()
+    assert O.rel_err(y0, O.inv_transform(Y, (D1, D2, D3), cmode=0, scale=1.0)) < TOL
+
+
+@pytest.mark.parametrize("B,Ci,Co,spatial,modes", [
+    (2, 3, 4, (10, 9), (3, 4)),
+    (5, 20, 20, (130, 130), (12, 12)),
+    (3, 7, 5, (34, 34), (6, 9)),
+    (2, 64, 64, (66, 66), (16, 16)),
+    (2, 3, 2, (8, 6, 10), (3, 2, 4)),
+    (1, 20, 20, (24, 24, 24), (12, 12, 12)),
+    (9, 4, 6, (12, 10, 14), (4, 3, 4)),
+])
+def test_mix_fwd_bwd(lib, B, Ci, Co, spatial, modes):
+    rng = np.random.default_rng(B * 100 + Ci)
+    nd = len(spatial)
+    plan = lib.get_plan(torch.device("cuda", 0), spatial, modes)
+    ws = [cplx(rng, (Ci, Co) + tuple(modes), scale=0.5) for _ in range(2 if nd == 2 else 4)]
+    X = cplx(rng, (B, Ci) + plan.spec_shape)
+    gY = cplx(rng, (B, Co) + plan.spec_shape)
+    wt = [dev(w) for w in ws]
+    Y = lib.mix_fwd(plan, dev(X), wt).cpu().numpy()
+    wcat = O.cat_corner_weights(ws)
+    assert O.rel_err(Y, O.mix_fwd(X.astype(np.complex128), wcat)) < TOL
+    gX, gws = lib.mix_bwd(plan, dev(X), dev(gY), wt)
+    gx_ref, gw_ref = O.mix_bwd(X.astype(np.complex128), gY.astype(np.complex128), wcat)
+    assert O.rel_err(gX.cpu().numpy(), gx_ref) < TOL
+    for got, ref in zip(gws, O.split_corner_grads(gw_ref, len(ws))):
+        assert O.rel_err(got.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("B,Co,Ci,spatial", [
+    (2, 20, 20, (130, 130)),
+    (3, 8, 8, (13, 11)),         # N not a multiple of 4 -> scalar path
+    (2, 6, 10, (16, 16)),        # Co != Ci
+    (1, 64, 64, (66, 66)),
+    (2, 20, 20, (16, 16, 22)),
+    (1, 5, 3, (9, 7)),           # channel counts that are not tile multiples
+])
+def test_pointwise_fwd_transpose_wgrad(lib, B, Co, Ci, spatial):
+    rng = np.random.default_rng(Co * 10 + Ci)
+    a = rng.standard_normal((B, Ci) + spatial).astype(np.float32)
+    w = rng.standard_normal((Co, Ci) + (1,) * len(spatial)).astype(np.float32)
+    b = rng.standard_normal(Co).astype(np.float32)
+    ds = rng.standard_normal((B, Co) + spatial).astype(np.float32)
+    out = lib.pointwise_fwd(dev(a), dev(w), dev(b)).cpu().numpy()
+    assert O.rel_err(out, O.pointwise_conv(a, w, b)) < TOL
+    w2 = w.reshape(Co, Ci).astype(np.float64)
+    back = lib.pointwise_fwd(dev(ds), dev(w), None, transpose=True).cpu().numpy()
+    assert O.rel_err(back, np.einsum("oi,bo...->bi...", w2, ds.astype(np.float64))) < TOL
+    gw, gb = lib.pointwise_wgrad(dev(ds), dev(a), w.shape)
+    ds2 = ds.reshape(B, Co, -1).astype(np.float64)
+    a2 = a.reshape(B, Ci, -1).astype(np.float64)
+    assert O.rel_err(gw.cpu().numpy().reshape(Co, Ci), np.einsum("bop,bip->oi", ds2, a2)) < TOL
+    assert O.rel_err(gb.cpu().numpy(), ds2.sum(axis=(0, 2))) < TOL
+
+
+def test_transform_properties_full_size(lib):
+    """Size-independent properties at the BASELINE cfg-1 plane size and a bench-sized batch:
+    linearity, adjointness <K1 x, Y> = <x, K1^H Y>, and exact recovery of a band-limited field."""
+    B, C, H, W, m = 16, 20, 130, 130, 12
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m, m))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x1 = torch.randn(B, C, H, W, device="cuda", generator=g)
+    x2 = torch.randn(B, C, H, W, device="cuda", generator=g)
+    X1, X2 = lib.fwd_transform(plan, x1), lib.fwd_transform(plan, x2)
+    X12 = lib.fwd_transform(plan, 0.5 * x1 - 2.0 * x2)
+    lin = (X12 - (0.5 * X1 - 2.0 * X2)).abs().max() / X12.abs().max()
+    assert lin.item() < TOL
+    Y = torch.randn(B, C, 2 * m, m, device="cuda", generator=g, dtype=torch.float32).to(torch.complex64)
+    Y = Y + 1j * torch.randn(B, C, 2 * m, m, device="cuda", generator=g)
+    lhs = (X1.to(torch.complex128) * Y.conj().to(torch.complex128)).real.sum()
+    rhs = (x1.double() * lib.inv_transform(plan, Y, cmode=0, scale=1.0).double()).sum()
+    assert abs(lhs.item() - rhs.item()) < 1e-5 * abs(lhs.item())
+    # A real field made only of retained modes is a fixed point of inverse(forward(.)).  The one
+    # retained mode whose Hermitian partner is NOT retained is (k1 = -m1, k2 = 0) (row m1 of the
+    # kept spectrum; +m1 is outside the low block), so it is zeroed before building the field.
+    Y[:, :, m, 0] = 0
+    band = lib.inv_transform(plan, Y, cmode=1)
+    again = lib.inv_transform(plan, lib.fwd_transform(plan, band), cmode=1)
+    assert ((again - band).abs().max() / band.abs().max()).item() < TOL
+
+
+def test_golden_spectral_kernels(lib, golden_spectral):
+    """The reference's own outputs (tests/golden/spectral_small.npz) through the raw kernels."""
+    from oracle.make_golden import SC2D_CASES
+
+    g = golden_spectral
+    for ci, (B, Ci, Co, H, W, m1, m2) in enumerate(SC2D_CASES):
+        pre = f"sc2d_{ci}_"
+        plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+        ws = [dev(g[pre + "w1"]), dev(g[pre + "w2"])]
+        X = lib.fwd_transform(plan, dev(g[pre + "x"]))
+        y = lib.inv_transform(plan, lib.mix_fwd(plan, X, ws), cmode=1)
+        assert O.rel_err(y.cpu().numpy(), g[pre + "y"]) < TOL
+
+
+def test_errors_are_loud(lib):
+    with pytest.raises(lib.FnoError):
+        lib.get_plan(torch.device("cuda", 0), (8, 8), (5, 3))       # 2*m1 > H
+    with pytest.raises(lib.FnoError):
+        lib.get_plan(torch.device("cuda", 0), (8, 8), (2, 6))       # m2 > W/2+1
+    with pytest.raises(lib.FnoError):
+        lib.get_plan(torch.device("cpu"), (8, 8), (2, 2))
+    plan = lib.get_plan(torch.device("cuda", 0), (8, 8), (2, 2))
+    with pytest.raises(lib.FnoError):
+        lib.fwd_transform(plan, torch.zeros(1, 1, 8, 8))            # CPU tensor
+    with pytest.raises(lib.FnoError):
+        lib.fwd_transform(plan, torch.zeros(1, 1, 8, 9, device="cuda"))
+    with pytest.raises(lib.FnoError):
+        lib.fwd_transform(plan, torch.zeros(1, 1, 8, 8, device="cuda", dtype=torch.float64))

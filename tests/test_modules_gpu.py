@@ -1,0 +1,225 @@
+"""Module-level parity of the drop-in FNO modules on a B200 against (a) the reference's golden
+vectors, (b) the fp64 dense-DFT oracle and (c) the torch port of the reference model run on the
+host CPU.  Tolerance (fp32 mode): max-abs-err / max-abs-ref <= 1e-5 on outputs and gradients."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dft_oracle as O
+from oracle import fno_port as P
+from oracle.make_golden import SC2D_CASES, SC3D_CASES, seeded
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("ci", range(len(SC2D_CASES)))
+def test_spectral_conv2d_module_vs_reference_golden(golden_spectral, ci):
+    from fno_b200.spectral import SpectralConv2d_fast
+
+    g = golden_spectral
+    B, Ci, Co, H, W, m1, m2 = SC2D_CASES[ci]
+    pre = f"sc2d_{ci}_"
+    mod = SpectralConv2d_fast(Ci, Co, m1, m2).cuda()
+    with torch.no_grad():
+        mod.weights1.copy_(dev(g[pre + "w1"]))
+        mod.weights2.copy_(dev(g[pre + "w2"]))
+    x = dev(g[pre + "x"]).requires_grad_(True)
+    y = mod(x)
+    y.backward(dev(g[pre + "g"]))
+    assert O.rel_err(y.detach().cpu().numpy(), g[pre + "y"]) < TOL
+    assert O.rel_err(x.grad.cpu().numpy(), g[pre + "gx"]) < TOL
+    assert O.rel_err(mod.weights1.grad.cpu().numpy(), g[pre + "gw1"]) < TOL
+    assert O.rel_err(mod.weights2.grad.cpu().numpy(), g[pre + "gw2"]) < TOL
+
+
+@pytest.mark.parametrize("ci", range(len(SC3D_CASES)))
+def test_spectral_conv3d_module_vs_reference_golden(golden_spectral, ci):
+    from fno_b200.spectral import SpectralConv3d
+
+    g = golden_spectral
+    B, Ci, Co, D1, D2, D3, m1, m2, m3 = SC3D_CASES[ci]
+    pre = f"sc3d_{ci}_"
+    mod = SpectralConv3d(Ci, Co, m1, m2, m3).cuda()
+    with torch.no_grad():
+        for k in range(1, 5):
+            getattr(mod, f"weights{k}").copy_(dev(g[pre + f"w{k}"]))
+    x = dev(g[pre + "x"]).requires_grad_(True)
+    y = mod(x)
+    y.backward(dev(g[pre + "g"]))
+    assert O.rel_err(y.detach().cpu().numpy(), g[pre + "y"]) < TOL
+    assert O.rel_err(x.grad.cpu().numpy(), g[pre + "gx"]) < TOL
+    for k in range(1, 5):
+        assert O.rel_err(getattr(mod, f"weights{k}").grad.cpu().numpy(), g[pre + f"gw{k}"]) < TOL
+
+
+def test_spectral_conv_cfg1_size_vs_reference_samples(golden_cfg1):
+    """C = 20, 130x130, modes 12 (BASELINE configs[0] trunk shape): sampled reference outputs."""
+    from fno_b200.fno import FNO2d
+
+    meta, arr = golden_cfg1
+    torch.manual_seed(meta["seed"])
+    model = FNO2d(**meta["ctor"]).cuda()
+    x = seeded((1, 20, 130, 130), 810).cuda().requires_grad_(True)
+    g = seeded((1, 20, 130, 130), 811).cuda()
+    y = model.conv0(x)
+    y.backward(g)
+    si, wi = arr["sc_idx"], arr["sc_widx"]
+    assert O.rel_err(y.detach().flatten().cpu().numpy()[si], arr["sc_y"]) < TOL
+    assert O.rel_err(x.grad.flatten().cpu().numpy()[si], arr["sc_gx"]) < TOL
+    assert O.rel_err(model.conv0.weights1.grad.flatten().cpu().numpy()[wi], arr["sc_gw1"]) < TOL
+    assert O.rel_err(model.conv0.weights2.grad.flatten().cpu().numpy()[wi], arr["sc_gw2"]) < TOL
+
+
+@pytest.mark.parametrize("gelu", [True, False])
+@pytest.mark.parametrize("shape,modes", [((2, 4, 10, 9), (3, 4)), ((1, 20, 34, 34), (12, 12)), ((1, 3, 8, 6, 10), (3, 2, 4))])
+def test_fourier_layer_vs_dense_oracle(shape, modes, gelu):
+    from fno_b200 import ops
+
+    rng = np.random.default_rng(5)
+    C = shape[1]
+    nd = len(modes)
+    a = rng.standard_normal(shape).astype(np.float32)
+    ws = [(0.2 * (rng.standard_normal((C, C) + modes) + 1j * rng.standard_normal((C, C) + modes))).astype(np.complex64)
+          for _ in range(2 if nd == 2 else 4)]
+    wl = (rng.standard_normal((C, C) + (1,) * nd) / np.sqrt(C)).astype(np.float32)
+    bl = rng.standard_normal(C).astype(np.float32)
+    g = rng.standard_normal(shape).astype(np.float32)
+    at = dev(a).requires_grad_(True)
+    wst = [dev(w).requires_grad_(True) for w in ws]
+    wlt, blt = dev(wl).requires_grad_(True), dev(bl).requires_grad_(True)
+    out = ops.fourier_layer(at, wlt, blt, gelu, wst)
+    out.backward(dev(g))
+    ref, _ = O.fourier_layer_forward(a, ws, wl, bl, gelu)
+    ga, gws, gwl, gbl = O.fourier_layer_backward(a, ws, wl, bl, gelu, g)
+    assert O.rel_err(out.detach().cpu().numpy(), ref) < TOL
+    assert O.rel_err(at.grad.cpu().numpy(), ga) < TOL
+    for t, r in zip(wst, gws):
+        assert O.rel_err(t.grad.cpu().numpy(), r) < TOL
+    assert O.rel_err(wlt.grad.cpu().numpy(), gwl) < TOL
+    assert O.rel_err(blt.grad.cpu().numpy(), gbl) < TOL
+
+
+def _load_params(model, golden, name):
+    pre = f"{name}_param_"
+    sd = {k[len(pre):]: torch.from_numpy(golden[k]) for k in golden.files if k.startswith(pre)}
+    for k in list(model.state_dict().keys()):
+        if k.startswith("shared_layers"):
+            # aliases of the trunk parameters (fno_aux): resolved through the primary names
+            continue
+        assert k in sd, k
+    model.load_state_dict(sd, strict=False)
+    return model
+
+
+@pytest.mark.parametrize("name", ["fno2d", "fno3d", "aux2d"])
+def test_models_vs_reference_golden(golden_models, name):
+    from fno_b200 import fno as F
+    from fno_b200 import fno_aux as FA
+
+    g = golden_models
+    if name == "fno2d":
+        model = F.FNO2d(num_channels=2, modes1=4, modes2=4, width=8, initial_step=3)
+        inputs = ("fno2d_x", "fno2d_grid")
+    elif name == "fno3d":
+        model = F.FNO3d(num_channels=3, modes1=3, modes2=3, modes3=3, width=6, initial_step=2)
+        inputs = ("fno3d_x", "fno3d_grid")
+    else:
+        model = FA.FNO2d(num_channels=2, modes1=4, modes2=4, width=8, initial_step=3)
+        inputs = ("aux2d_x", "aux2d_grid", "aux2d_xa", "aux2d_ga")
+    model = _load_params(model, g, name).cuda()
+    outs = model(*[dev(g[k]) for k in inputs])
+    if not isinstance(outs, tuple):
+        outs = (outs,)
+    loss = 0.0
+    for k, o in enumerate(outs):
+        assert O.rel_err(o.detach().cpu().numpy(), g[f"{name}_out{k}"]) < TOL
+        loss = loss + (o * dev(g[f"{name}_g{k}"])).sum()
+    loss.backward()
+    params = dict(model.named_parameters())
+    pre = f"{name}_grad_"
+    n = 0
+    for k in g.files:
+        if k.startswith(pre):
+            # weight/bias gradients are long cancelling fp32 sums on both sides: 2e-5
+            assert O.rel_err(params[k[len(pre):]].grad.cpu().numpy(), g[k]) < 2e-5, k
+            n += 1
+    assert n >= 6
+
+
+def test_fno2d_cfg1_vs_reference_samples(golden_cfg1):
+    """BASELINE configs[0] at full size (128x128, modes 12, width 20): forward samples, nRMSE loss
+    and every parameter-gradient norm against the unmodified reference (seed 16)."""
+    from fno_b200.fno import FNO2d
+
+    meta, arr = golden_cfg1
+    torch.manual_seed(meta["seed"])
+    model = FNO2d(**meta["ctor"])
+    for k, fp in meta["params"].items():
+        t = model.state_dict()[k]
+        r = (torch.view_as_real(t) if t.is_complex() else t).double().flatten()
+        assert [float(v) for v in r[:4]] == fp["head"], k      # same RNG stream as the reference
+    model = model.cuda()
+    B = 2
+    x = seeded((B, 128, 128, 10, 2), 800).cuda()
+    lin = torch.linspace(-1 + 1 / 128, 1 - 1 / 128, 128)
+    gx, gy = torch.meshgrid(lin, lin, indexing="ij")
+    grid = torch.stack((gx, gy), dim=-1).unsqueeze(0).repeat(B, 1, 1, 1).cuda()
+    yy = seeded((B, 128, 128, 1, 2), 801).cuda()
+    out = model(x, grid)
+    loss = P.nrmse(out, yy).mean()
+    loss.backward()
+    assert O.rel_err(out.detach().flatten().cpu().numpy()[arr["out_idx"]], arr["out_val"]) < TOL
+    assert abs(loss.item() - meta["cfg1_loss"]) < 1e-5 * meta["cfg1_loss"]
+    for k, p in model.named_parameters():
+        ref = meta["cfg1_grad_norms"][k]
+        assert abs(float(torch.norm(p.grad, 2)) - ref) < 2e-5 * max(ref, 1e-12), k
+    assert O.rel_err(model.conv1.weights1.grad.flatten().cpu().numpy()[arr["conv1_w1_grad_idx"]],
+                     arr["conv1_w1_grad_val"]) < 2e-5
+    assert O.rel_err(model.w2.weight.grad.cpu().numpy(), arr["w2_weight_grad"]) < 2e-5
+    assert O.rel_err(model.fc0.weight.grad.cpu().numpy(), arr["fc0_weight_grad"]) < 2e-5
+
+
+def test_fno3d_vs_cpu_port():
+    """FNO3d on a mid-size volume with reference padding (last axis + 6) vs the torch port on CPU."""
+    from fno_b200.fno import FNO3d
+
+    torch.manual_seed(16)
+    model = FNO3d(num_channels=2, modes1=4, modes2=4, modes3=4, width=8, initial_step=3)
+    p = P.as_leaves({k: v for k, v in model.state_dict().items()})
+    x = seeded((2, 16, 16, 12, 3, 2), 50)
+    grid = torch.rand(2, 16, 16, 12, 3, generator=torch.Generator().manual_seed(51))
+    g = seeded((2, 16, 16, 12, 1, 2), 52)
+    ref = P.fno_forward(p, x, grid)
+    (ref * g).sum().backward()
+    model = model.cuda()
+    out = model(x.cuda(), grid.cuda())
+    (out * g.cuda()).sum().backward()
+    assert O.rel_err(out.detach().cpu().numpy(), ref.detach().numpy()) < TOL
+    for k, q in model.named_parameters():
+        if q.grad is None:
+            assert k.startswith("bn")   # dead BatchNorm3d modules get no gradient (fno.py:334-337)
+            continue
+        assert O.rel_err(q.grad.cpu().numpy(), p[k].grad.numpy()) < 2e-5, k
+
+
+def test_eval_and_train_step_run_without_host_sync_errors():
+    """Smoke: no_grad forward keeps no autograd state; a full optimizer step updates cfloat params."""
+    from fno_b200.fno import FNO2d
+
+    torch.manual_seed(0)
+    model = FNO2d(num_channels=2, modes1=4, modes2=4, width=8, initial_step=3).cuda()
+    x = torch.randn(2, 16, 16, 3, 2, device="cuda")
+    grid = torch.rand(2, 16, 16, 2, device="cuda")
+    with torch.no_grad():
+        y0 = model(x, grid)
+    assert not y0.requires_grad
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    before = model.conv2.weights1.detach().clone()
+    loss = P.nrmse(model(x, grid), torch.randn_like(y0)).mean()
+    P.train_step_tail(loss, model.parameters(), opt)
+    assert (model.conv2.weights1.detach() - before).abs().max().item() > 0
