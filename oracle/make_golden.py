@@ -21,7 +21,10 @@ import numpy as np
 import torch
 
 REF = Path("/root/reference/pdebench/models")
-OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "tests" / "golden"
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
 
 
 def _import_reference():
@@ -189,10 +192,23 @@ def gen_cfg1(ref_fno, ref_aux):
     loss.backward()
     idx = sample_index(out.numel(), 4096)
     arrays = {"out_idx": idx, "out_val": out.detach().flatten().numpy()[idx]}
-    meta["cfg1_loss"] = float(loss)
+    meta["cfg1_loss"] = float(loss.detach())
     meta["cfg1_out_sum"] = float(out.double().sum())
     meta["cfg1_grad_norms"] = {k: float(torch.norm(p.grad.detach(), 2)) for k, p in m.named_parameters()}
+    # the same step through the fp64 port (oracle/fno_port.py): the fp32 reference's own gradient
+    # norms deviate from these by up to ~4e-5 relative (its noise floor), so tight checks of the
+    # CUDA path use the fp64 numbers and the fp32 ones are only a sanity band
+    from oracle import fno_port as P
+    p64 = P.as_leaves({k: v for k, v in m.state_dict().items()}, dtype=torch.float64)
+    out64 = P.fno_forward(p64, x.double(), grid.double())
+    loss64 = P.nrmse(out64, yy.double()).mean()
+    loss64.backward()
+    meta["cfg1_loss_fp64"] = float(loss64.detach())
+    meta["cfg1_grad_norms_fp64"] = {k: float(torch.norm(p64[k].grad, 2)) for k, _ in m.named_parameters()}
     gidx = sample_index(m.conv1.weights1.numel(), 2048, seed=77)
+    arrays["conv1_w1_grad_val_fp64"] = p64["conv1.weights1"].grad.flatten().numpy()[gidx]
+    arrays["w2_weight_grad_fp64"] = p64["w2.weight"].grad.numpy()
+    arrays["fc0_weight_grad_fp64"] = p64["fc0.weight"].grad.numpy()
     arrays["conv1_w1_grad_idx"] = gidx
     arrays["conv1_w1_grad_val"] = m.conv1.weights1.grad.flatten().numpy()[gidx]
     arrays["w2_weight_grad"] = m.w2.weight.grad.numpy()

@@ -347,12 +347,15 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
 }
 
 inline int round_threads(int n) { return (n + 31) & ~31; }
+constexpr size_t kMaxOptinSmem = 227 * 1024;  // sm_100: 232448 B opt-in per CTA
 
 template <int M1T>
 int dispatch_fwd(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
                  int cmode, float scale, cudaStream_t st, bool attr_only) {
   const int threads = round_threads(p->G_fwd * p->W);
-  const size_t smem = fwd_smem_bytes(p, p->G_fwd);
+  // attr_only: opt every instantiation this plan can reach into the device maximum once; the
+  // limit is per kernel function, so it must never be lowered by a later, smaller plan
+  const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, p->G_fwd);
   if (threads <= 288)
     return launch_fwd_t<M1T, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
   if (threads <= 576)
@@ -364,7 +367,7 @@ template <int M1T>
 int dispatch_inv(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                  int cmode, float scale, int apply_gelu, cudaStream_t st, bool attr_only) {
   const int threads = round_threads(p->G_inv * p->W);
-  const size_t smem = inv_smem_bytes(p, p->G_inv);
+  const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, p->G_inv);
   if (threads <= 288)
     return launch_inv_t<M1T, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
   if (threads <= 576)

@@ -175,13 +175,19 @@ def test_fno2d_cfg1_vs_reference_samples(golden_cfg1):
     loss.backward()
     assert O.rel_err(out.detach().flatten().cpu().numpy()[arr["out_idx"]], arr["out_val"]) < TOL
     assert abs(loss.item() - meta["cfg1_loss"]) < 1e-5 * meta["cfg1_loss"]
+    # Gradients: the tight 1e-5 check is against the fp64 port of the same step; the fp32
+    # reference's own norms sit up to ~4e-5 away from fp64 (its rounding noise), so they only
+    # bound a 1e-4 sanity band.
     for k, p in model.named_parameters():
-        ref = meta["cfg1_grad_norms"][k]
-        assert abs(float(torch.norm(p.grad, 2)) - ref) < 2e-5 * max(ref, 1e-12), k
+        got = float(torch.norm(p.grad, 2))
+        ref64, ref32 = meta["cfg1_grad_norms_fp64"][k], meta["cfg1_grad_norms"][k]
+        assert abs(got - ref64) < 1e-5 * max(ref64, 1e-12), k
+        assert abs(got - ref32) < 1e-4 * max(ref32, 1e-12), k
     assert O.rel_err(model.conv1.weights1.grad.flatten().cpu().numpy()[arr["conv1_w1_grad_idx"]],
-                     arr["conv1_w1_grad_val"]) < 2e-5
-    assert O.rel_err(model.w2.weight.grad.cpu().numpy(), arr["w2_weight_grad"]) < 2e-5
-    assert O.rel_err(model.fc0.weight.grad.cpu().numpy(), arr["fc0_weight_grad"]) < 2e-5
+                     arr["conv1_w1_grad_val_fp64"]) < TOL
+    assert O.rel_err(model.w2.weight.grad.cpu().numpy(), arr["w2_weight_grad_fp64"]) < TOL
+    assert O.rel_err(model.fc0.weight.grad.cpu().numpy(), arr["fc0_weight_grad_fp64"]) < TOL
+    assert O.rel_err(model.w2.weight.grad.cpu().numpy(), arr["w2_weight_grad"]) < 1e-4
 
 
 def test_fno3d_vs_cpu_port():
