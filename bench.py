@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py -- FNO2d train samples/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B_per_gpu] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[0] -- FNO2d(modes 12, width 20, initial_step 10,
+2 channels) on 2-D diffusion-reaction-shaped 128x128 fields, one full training step exactly as
+fno/train.py:264-278 (forward, nRMSE loss, backward, adaptive grad-norm clip, Adam(wd 1e-4),
+cosine LR), synthetic data, random-init weights (seed 16).  fp32 end to end.
+
+Keys beyond the base contract:
+  value     whole-job samples/s with inputs already resident in HBM (device-timed, max over ranks)
+  e2e       same metric through the public module API with HOST pinned inputs: per step an H2D
+            copy of (xx, yy, grid) and a D2H read of the loss, copies prefetched on a side stream
+  roofline  the dominant libfno_sm100 kernel: algorithmic bytes per launch / its mean launch time
+            (CUDA events on the launching stream, measured live in a separate instrumented pass)
+            against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  the oracle port of the reference step (oracle/fno_port.py) on the host cores
+  --impl reference: times that CPU port alone (rank 0 only under torchrun).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (ROOT, ROOT / "sciml-pde_b200"):
+    if str(_p) not in sys.path:
+        sys.path.insert(0, str(_p))
+
+import torch  # noqa: E402
+
+CFG = dict(num_channels=2, modes1=12, modes2=12, width=20, initial_step=10)
+RES = 128
+WORKLOAD = "FNO2d m12 w20 init10, 2D diffusion-reaction 128x128x2ch (BASELINE configs[0]), full train step"
+METRIC = "FNO2d train samples/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=128, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference training step
+# ------------------------------------------------------------------------------------------------
+def cpu_port_run(batch: int, steps: int, warmup: int):
+    """Times the reference algorithm (oracle/fno_port.py: torch.fft + einsum + conv, train.py step
+    tail) on the host cores.  Returns (samples_per_s, ms_per_step, cores)."""
+    from fno_b200 import data
+    from oracle import fno_port as P
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(16)
+    params = P.as_leaves(P.init_params(2, CFG["num_channels"], (CFG["modes1"], CFG["modes2"]), CFG["width"],
+                                       CFG["initial_step"]))
+    leaves = [v for v in params.values() if v.requires_grad]
+    opt = torch.optim.Adam(leaves, lr=1e-3, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=1000)
+    xx, yy, grid = data.synthetic_batch(batch, RES, CFG["initial_step"], CFG["num_channels"], seed=0)
+
+    def step():
+        loss = P.nrmse(P.fno_forward(params, xx, grid), yy).mean()
+        P.train_step_tail(loss, leaves, opt, sched)
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, 1e3 * dt / steps, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    v, ms, cores = cpu_port_run(args.cpu_batch, steps, warmup)
+    sample = f"{steps} timed + {warmup} warm-up steps of batch {args.cpu_batch} (same model/config, host CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 3), "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_step_batch": args.cpu_batch, "device": "host CPU"},
+        "cpu_baseline": {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": round(v, 3), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel event timing (roofline)
+# ------------------------------------------------------------------------------------------------
+class KernelTimer:
+    """Wraps the fno_b200.lib call wrappers with CUDA events on the current stream."""
+
+    NAMES = ["fwd_transform", "inv_transform", "mix_fwd", "mix_bwd", "pointwise_fwd", "pointwise_wgrad"]
+
+    def __init__(self, lib):
+        self.lib = lib
+        self.records = []
+        self.saved = {}
+
+    def __enter__(self):
+        for name in self.NAMES:
+            fn = getattr(self.lib, name)
+            self.saved[name] = fn
+            setattr(self.lib, name, self._wrap(name, fn))
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self.saved.items():
+            setattr(self.lib, name, fn)
+
+    def _wrap(self, name, fn):
+        def inner(*a, **k):
+            tag = name
+            if name == "fwd_transform" and k.get("preact") is not None:
+                tag = "fwd_transform+gelu_grad"
+            if name == "inv_transform":
+                tag = "inv_transform+bypass" + ("+gelu" if k.get("apply_gelu") else "") if k.get("addend") is not None else "inv_transform"
+                if k.get("s_out") is not None:
+                    tag += "+preact"
+            if name == "pointwise_fwd" and k.get("transpose"):
+                tag = "pointwise_bwd_data"
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            self.records.append((tag, e0, e1))
+            return out
+        return inner
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, e0, e1 in self.records:
+            d = agg.setdefault(tag, [0.0, 0])
+            d[0] += e0.elapsed_time(e1)
+            d[1] += 1
+        return {k: {"ms_total": v[0], "launches": v[1], "ms_avg": v[0] / v[1]} for k, v in agg.items()}
+
+
+def algorithmic_bytes(tag: str, B: int) -> int:
+    """Per-launch algorithmic bytes of each kernel at the bench workload:
+    every input read once, every output written once, weights once per launch."""
+    C, N, M = CFG["width"], (RES + 2) * (RES + 2), 2 * CFG["modes1"] * CFG["modes2"]
+    act, spec, wts = 4 * C * N * B, 8 * C * M * B, 8 * C * C * M
+    table = {
+        "fwd_transform": act + spec,
+        "fwd_transform+gelu_grad": 3 * act + spec,                 # reads g, s; writes dS; + gY
+        "inv_transform": spec + act,
+        "inv_transform+bypass": spec + 2 * act,                    # layer 3 fwd / layer bwd: read addend, write out
+        "inv_transform+bypass+gelu": spec + 2 * act,
+        "inv_transform+bypass+gelu+preact": spec + 3 * act,        # + store of the pre-activation
+        "inv_transform+bypass+preact": spec + 3 * act,
+        "mix_fwd": 2 * spec + wts,
+        "mix_bwd": 4 * spec + 2 * wts,                             # data-grad + weight-grad launches together
+        "pointwise_fwd": 2 * act,
+        "pointwise_bwd_data": 2 * act,
+        "pointwise_wgrad": 2 * act,
+    }
+    return table[tag]
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    from fno_b200 import data, lib
+    from fno_b200.dp import BucketedGradAllReduce
+    from fno_b200.fno import FNO2d
+    from fno_b200.train import TrainStep
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: libfno_sm100 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+
+    torch.manual_seed(16)
+    model = FNO2d(**CFG).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100000)
+    dp = BucketedGradAllReduce(model) if world > 1 else None
+    step = TrainStep(model, opt, sched, dp=dp)
+
+    # two distinct host batches per rank (pinned); device copies for the HBM-resident measurement
+    host = []
+    for i in range(2):
+        xx, yy, grid = data.synthetic_batch(B, RES, CFG["initial_step"], CFG["num_channels"], seed=1000 * rank + i)
+        host.append(tuple(t.pin_memory() for t in (xx, yy, grid)))
+    devb = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------
+    for i in range(W):
+        step(*devb[i % 2])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        loss = step(*devb[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.launch_count() - l0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    final_loss = float(loss)
+
+    # ---- end to end: host-pinned inputs, prefetch on a copy stream, loss read back every step ----
+    e2e = None
+    if not args.no_e2e:
+        copy_stream = torch.cuda.Stream()
+        bufs = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                for dst, src in zip(bufs[i % 2], host[i % 2]):
+                    dst.copy_(src, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(n):
+            cur = torch.cuda.current_stream()
+            for s in range(2):
+                consumed[s].record(cur)
+            prefetch(0)
+            last = 0.0
+            for i in range(n):
+                if i + 1 < n:
+                    prefetch(i + 1)
+                cur.wait_event(ready[i % 2])
+                loss_i = step(*bufs[i % 2])
+                consumed[i % 2].record(cur)
+                last = float(loss_i)          # D2H read of the step's loss (4 bytes) -> host sync
+            return last
+
+        e2e_loop(W)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        e2e_loop(K)
+        t1.record()
+        torch.cuda.synchronize()
+        ms_e2e = max_over_ranks(t0.elapsed_time(t1))
+        barrier()
+        e2e = {"value": round(world * B * K / (ms_e2e / 1e3), 2), "unit": "samples/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3)}
+
+    # ---- instrumented pass: per-kernel CUDA events (never used for `value`) -------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    nprof = min(K, 5)
+    with KernelTimer(lib) as kt:
+        for i in range(nprof):
+            step(*devb[i % 2])
+        ksum = kt.summary()
+    barrier()
+    if rank == 0:
+        kernels = {}
+        for tag, r in sorted(ksum.items(), key=lambda kv: -kv[1]["ms_total"]):
+            nbytes = algorithmic_bytes(tag, B)
+            kernels[tag] = {"ms_avg": round(r["ms_avg"], 4), "launches_per_step": r["launches"] / nprof,
+                            "gbs": round(nbytes / (r["ms_avg"] * 1e-3) / 1e9, 1),
+                            "ms_per_step": round(r["ms_total"] / nprof, 3)}
+        top = next(iter(kernels))
+        roofline = {"bound": "hbm", "kernel": top, "achieved": kernels[top]["gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": round(kernels[top]["gbs"] / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": algorithmic_bytes(top, B)}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms, cores = cpu_port_run(args.cpu_batch, 6, 2)
+        cpu = {"value": round(v, 3), "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"6 timed + 2 warm-up full training steps of batch {args.cpu_batch} on the host CPU "
+                         f"(oracle/fno_port.py, torch {torch.__version__})", "ms_per_step": round(ms, 2)}
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    value = world * B * K / (ms_total / 1e3)
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
+                   "parallelism": f"dp{world}" if world > 1 else "single",
+                   "l2_policy": f"inputs larger than L2: two alternating {h2d_bytes / 1e6:.0f} MB input batches, "
+                                f"{4 * CFG['width'] * (RES + 2) ** 2 * B / 1e6:.0f} MB per activation tensor"},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "kernels": kernels, "final_loss": round(final_loss, 6),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,28 +93,38 @@ int launch_pw(const float* in, const float* Wm, const float* bias, float* out, i
 // ------------------------------------------------------------------------------------------
 constexpr int KT = 128;      // pixels per shared-memory slab
 constexpr int WG_T = 10;     // output tile edge per warp (register tile T x T)
-constexpr int WG_MAXW = 16;  // warps per CTA (max tiles per CTA)
+constexpr int WG_MAXW = 8;   // warps (= output tiles) per CTA
 
-// part[(b * chunks + chunk)][Co][Ci + 1]  (last column: bias gradient)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(d), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Persistent split-K: CTA c owns the contiguous slab range [c*spc, (c+1)*spc) of the B*slabs_per_sample
+// slabs (slab = KT consecutive pixels of one sample, all channels of ds and a).  Slabs stream through
+// a 2-stage cp.async ring (16-byte copies, zero-filled past the end of the sample).
+// part[cta][Co][Ci + 1]  (last column: bias gradient)
 template <int T>
 __global__ void __launch_bounds__(32 * WG_MAXW)
 wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part,
-                     int Co, int Ci, long N, long chunk_len, int tiles_i, int ntiles) {
-  extern __shared__ __align__(16) float sm[];  // [Co][KT] ds slab, [Ci][KT] a slab
-  float* ds_s = sm;
-  float* a_s = sm + (size_t)Co * KT;
+                     int Co, int Ci, long N, int slabs_per_sample, long total_slabs, long slabs_per_cta,
+                     int tiles_i, int ntiles, int aligned) {
+  extern __shared__ __align__(16) float sm[];  // 2 stages x ([Co][KT] ds slab, [Ci][KT] a slab)
+  const int rows = Co + Ci;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
-  const int b = blockIdx.y;
-  const long k_begin = (long)blockIdx.x * chunk_len;
-  long k_end = k_begin + chunk_len;
-  if (k_end > N) k_end = N;
-  const int tile = blockIdx.z * nwarps + warp;
+  const int tile = blockIdx.y * nwarps + warp;
   const bool has_tile = tile < ntiles;
   const int to = has_tile ? (tile / tiles_i) * T : 0;
   const int ti = has_tile ? (tile % tiles_i) * T : 0;
   const bool bias_tile = has_tile && (ti == 0);
+  long s_begin = (long)blockIdx.x * slabs_per_cta;
+  long s_end = s_begin + slabs_per_cta;
+  if (s_end > total_slabs) s_end = total_slabs;
 
   float acc[T][T];
   float accb[T];
@@ -124,22 +134,46 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
 #pragma unroll
     for (int c = 0; c < T; ++c) acc[r][c] = 0.f;
   }
-  const float* __restrict__ dsb = ds + (size_t)b * Co * N;
-  const float* __restrict__ ab = a + (size_t)b * Ci * N;
-  for (long k0 = k_begin; k0 < k_end; k0 += KT) {
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < Co * KT; idx += blockDim.x) {
-      const int c = idx / KT, kk = idx - c * KT;
-      const long k = k0 + kk;
-      ds_s[idx] = (k < k_end) ? __ldg(dsb + (size_t)c * N + k) : 0.f;
+
+  auto issue = [&](long slab, int stage) {
+    float* dst = sm + (size_t)stage * rows * KT;
+    const long b = slab / slabs_per_sample;
+    const long k0 = (slab - b * slabs_per_sample) * KT;
+    const float* dsb = ds + (size_t)b * Co * N;
+    const float* ab = a + (size_t)b * Ci * N;
+    if (aligned) {
+      for (int idx = threadIdx.x; idx < rows * (KT / 4); idx += blockDim.x) {
+        const int c = idx / (KT / 4), q = idx - c * (KT / 4);
+        const long k = k0 + 4 * q;
+        const float* src = (c < Co) ? (dsb + (size_t)c * N + k) : (ab + (size_t)(c - Co) * N + k);
+        long left = (N - k) * 4;
+        const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+        cp_async16(dst + c * KT + 4 * q, nb > 0 ? src : ds, nb);
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < rows * KT; idx += blockDim.x) {
+        const int c = idx / KT, kk = idx - c * KT;
+        const long k = k0 + kk;
+        const float* src = (c < Co) ? (dsb + (size_t)c * N + k) : (ab + (size_t)(c - Co) * N + k);
+        dst[idx] = (k < N) ? __ldg(src) : 0.f;
+      }
     }
-    for (int idx = threadIdx.x; idx < Ci * KT; idx += blockDim.x) {
-      const int c = idx / KT, kk = idx - c * KT;
-      const long k = k0 + kk;
-      a_s[idx] = (k < k_end) ? __ldg(ab + (size_t)c * N + k) : 0.f;
+    cp_async_commit();
+  };
+
+  if (s_begin < s_end) issue(s_begin, 0);
+  for (long slab = s_begin; slab < s_end; ++slab) {
+    const int stage = (int)((slab - s_begin) & 1);
+    if (slab + 1 < s_end) {
+      issue(slab + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     if (has_tile) {
+      const float* ds_s = sm + (size_t)stage * rows * KT;
+      const float* a_s = ds_s + (size_t)Co * KT;
 #pragma unroll
       for (int kk = 0; kk < KT; kk += 32) {
         float dv[T], av[T];
@@ -155,9 +189,10 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
         }
       }
     }
+    __syncthreads();  // the stage is refilled by the next iteration's issue()
   }
   if (!has_tile) return;
-  float* __restrict__ pp = part + ((size_t)b * gridDim.x + blockIdx.x) * Co * (Ci + 1);
+  float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
 #pragma unroll
   for (int r = 0; r < T; ++r) {
 #pragma unroll
@@ -176,13 +211,19 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gW, float* __restrict__ gb,
-                                    int nparts, int Co, int Ci) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output element: lanes stride the per-CTA partials, fixed-order shuffle tree
+__global__ void __launch_bounds__(128)
+wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gW, float* __restrict__ gb, int nparts,
+                    int Co, int Ci) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int total = Co * (Ci + 1);
   if (idx >= total) return;
   float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(size_t)p * total + idx];
+  for (int p = lane; p < nparts; p += 32) s += part[(size_t)p * total + idx];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane != 0) return;
   const int o = idx / (Ci + 1), i = idx - o * (Ci + 1);
   if (i < Ci) {
     if (gW != nullptr) gW[(size_t)o * Ci + i] = s;
@@ -191,13 +232,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ part, float* __res
   }
 }
 
-int wgrad_chunks(long N) {
-  // enough CTAs per sample to fill the machine at small batch, but >= 4 slabs of work each
-  long c = (N + 4 * KT - 1) / (4 * KT);
-  if (c > 8) c = 8;
-  if (c < 1) c = 1;
-  return (int)c;
-}
+constexpr int WG_CTAS = 148 * 2;  // persistent grid: 2 resident CTAs per SM (register-limited)
 
 }  // namespace
 }  // namespace fno
@@ -228,7 +263,7 @@ extern "C" int fno_pointwise_fwd(const float* in, const float* W, const float* b
 
 extern "C" size_t fno_pointwise_wgrad_workspace_bytes(int B, int Co, int Ci, long N) {
   if (B <= 0 || Co <= 0 || Ci <= 0 || N <= 0) return 0;
-  return sizeof(float) * (size_t)B * wgrad_chunks(N) * Co * (Ci + 1);
+  return sizeof(float) * (size_t)WG_CTAS * Co * (Ci + 1);
 }
 
 extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B, int Co,
@@ -237,33 +272,36 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
     set_error("fno_pointwise_wgrad: bad argument");
     return FNO_E_ARG;
   }
-  if (B > 65535) { set_error("fno_pointwise_wgrad: batch %d > 65535", B); return FNO_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int chunks = wgrad_chunks(N);
-  long chunk_len = (N + chunks - 1) / chunks;
-  chunk_len = ((chunk_len + KT - 1) / KT) * KT;
   constexpr int T = WG_T;
   const int tiles_o = (Co + T - 1) / T, tiles_i = (Ci + T - 1) / T;
   const int ntiles = tiles_o * tiles_i;
   const int warps = ntiles < WG_MAXW ? ntiles : WG_MAXW;
-  const int zgroups = (ntiles + warps - 1) / warps;
-  const size_t smem = sizeof(float) * (size_t)(Co + Ci) * KT;
+  const int ygroups = (ntiles + warps - 1) / warps;
+  const size_t smem = sizeof(float) * 2ul * (size_t)(Co + Ci) * KT;
   if (smem > 200 * 1024) { set_error("fno_pointwise_wgrad: width %d too large", Co + Ci); return FNO_E_ARG; }
-  static std::atomic<size_t> attr_set{0};
-  if (smem > 48 * 1024 && attr_set.load() < smem) {
-    if (cudaFuncSetAttribute(wgrad_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+  static std::atomic<int> attr_done{0};
+  if (!attr_done.load()) {
+    if (cudaFuncSetAttribute(wgrad_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess)
       return check_launch("cudaFuncSetAttribute(wgrad)");
-    attr_set.store(smem);
+    attr_done.store(1);
   }
+  const int slabs_per_sample = (int)((N + KT - 1) / KT);
+  const long total_slabs = (long)B * slabs_per_sample;
+  long ctas = total_slabs < WG_CTAS ? total_slabs : WG_CTAS;
+  const long spc = (total_slabs + ctas - 1) / ctas;
+  ctas = (total_slabs + spc - 1) / spc;
+  const int aligned = (N % 4 == 0) && ((reinterpret_cast<size_t>(ds) | reinterpret_cast<size_t>(a)) % 16 == 0);
   float* part = static_cast<float*>(work);
-  dim3 grid(chunks, B, zgroups);
-  wgrad_partial_kernel<T><<<grid, 32 * warps, smem, st>>>(ds, a, part, Co, Ci, N, chunk_len, tiles_i, ntiles);
+  dim3 grid((unsigned)ctas, ygroups);
+  wgrad_partial_kernel<T><<<grid, 32 * warps, smem, st>>>(ds, a, part, Co, Ci, N, slabs_per_sample, total_slabs, spc,
+                                                        tiles_i, ntiles, aligned);
   count_launch();
   int rc = check_launch("wgrad_partial_kernel");
   if (rc != FNO_OK) return rc;
   const int total = Co * (Ci + 1);
-  wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, st>>>(part, gW, gb, B * chunks, Co, Ci);
+  wgrad_reduce_kernel<<<(total * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas, Co, Ci);
   count_launch();
   return check_launch("wgrad_reduce_kernel");
 }

@@ -21,6 +21,8 @@
 //
 // Several planes are flattened into one CTA (thread <-> (g, w), g < G) so that widths like
 // 130 = 4*32+2 do not waste a nearly empty warp per plane.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fno {
@@ -107,8 +109,22 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
     // h = 0 (self-paired)
     fold_accumulate<M1T>(acc, twH_s, load(0), 0.0f);
     const int npairs = (H - 1) / 2;
-#pragma unroll 2
-    for (int t = 1; t <= npairs; ++t) {
+    // PG row pairs per step: all 2*PG global loads are issued before the FMAs that consume them,
+    // which is what keeps enough bytes in flight per SM (the kernel has no other latency hiding
+    // than its own memory-level parallelism and the other resident warps)
+    constexpr int PG = 4;
+    int t = 1;
+    for (; t + PG - 1 <= npairs; t += PG) {
+      float v1[PG], v2[PG];
+#pragma unroll
+      for (int u = 0; u < PG; ++u) {
+        v1[u] = load(t + u);
+        v2[u] = load(H - t - u);
+      }
+#pragma unroll
+      for (int u = 0; u < PG; ++u) fold_accumulate<M1T>(acc, twH_s + (t + u) * JP, v1[u] + v2[u], v1[u] - v2[u]);
+    }
+    for (; t <= npairs; ++t) {
       const float v1 = load(t);
       const float v2 = load(H - t);
       fold_accumulate<M1T>(acc, twH_s + t * JP, v1 + v2, v1 - v2);
@@ -246,9 +262,10 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
 
   // stage B: H-axis pass, two rows per step, fused epilogue
   const size_t base = (size_t)plane * H * W + w;
+  const bool has_add = addend != nullptr;
+  auto ld_add = [&](int h) -> float { return has_add ? addend[base + (size_t)h * W] : 0.f; };
   auto emit = [&](int h, float v) {
     const size_t idx = base + (size_t)h * W;
-    if (addend != nullptr) v += addend[idx];
     if (s_out != nullptr) s_out[idx] = v;
     if (apply_gelu) v = gelu_exact(v);
     out[idx] = v;
@@ -275,21 +292,51 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
   };
   {
     float e, o;
+    const float a0 = ld_add(0);
     eval(0, e, o);
-    emit(0, e);
+    emit(0, e + a0);
   }
   const int npairs = (H - 1) / 2;
-#pragma unroll 2
-  for (int t = 1; t <= npairs; ++t) {
+  // `addend` may alias `out` (in-place epilogue), so the compiler cannot move a load above an
+  // earlier store; the loads of a whole group of PG row pairs are therefore issued by hand before
+  // any of the group's stores, and the next group's loads before this group's arithmetic.
+  constexpr int PG = 4;
+  int t = 1;
+  float a1[PG], a2[PG];
+  if (t + PG - 1 <= npairs) {
+#pragma unroll
+    for (int u = 0; u < PG; ++u) { a1[u] = ld_add(t + u); a2[u] = ld_add(H - t - u); }
+  }
+  for (; t + PG - 1 <= npairs; t += PG) {
+    float n1[PG], n2[PG];
+    const bool more = (t + 2 * PG - 1 <= npairs);
+#pragma unroll
+    for (int u = 0; u < PG; ++u) {
+      n1[u] = more ? ld_add(t + PG + u) : 0.f;
+      n2[u] = more ? ld_add(H - t - PG - u) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < PG; ++u) {
+      float e, o;
+      eval(t + u, e, o);
+      emit(t + u, e + o + a1[u]);
+      emit(H - t - u, e - o + a2[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < PG; ++u) { a1[u] = n1[u]; a2[u] = n2[u]; }
+  }
+  for (; t <= npairs; ++t) {
     float e, o;
+    const float b1 = ld_add(t), b2 = ld_add(H - t);
     eval(t, e, o);
-    emit(t, e + o);
-    emit(H - t, e - o);
+    emit(t, e + o + b1);
+    emit(H - t, e - o + b2);
   }
   if ((H & 1) == 0) {
     float e, o;
+    const float b1 = ld_add(H / 2);
     eval(H / 2, e, o);
-    emit(H / 2, e);
+    emit(H / 2, e + b1);
   }
 }
 
@@ -357,7 +404,7 @@ int dispatch_fwd(const Plan* p, const float* x, const float* preact, float* ds_o
   // limit is per kernel function, so it must never be lowered by a later, smaller plan
   const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, p->G_fwd);
   if (threads <= 288)
-    return launch_fwd_t<M1T, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+    return launch_fwd_t<M1T, 288, 3>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
   if (threads <= 576)
     return launch_fwd_t<M1T, 576, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
   return launch_fwd_t<M1T, 1024, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
@@ -369,7 +416,7 @@ int dispatch_inv(const Plan* p, const float* Y, const float* addend, float* s_ou
   const int threads = round_threads(p->G_inv * p->W);
   const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, p->G_inv);
   if (threads <= 288)
-    return launch_inv_t<M1T, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+    return launch_inv_t<M1T, 288, 3>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
   if (threads <= 576)
     return launch_inv_t<M1T, 576, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
   return launch_inv_t<M1T, 1024, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
@@ -411,17 +458,26 @@ int setup_transform2d_attrs(const Plan* pc) {
   Plan* p = const_cast<Plan*>(pc);
   const size_t kMaxSmem = 200 * 1024;
   auto pick = [&](bool fwd) {
-    // aim for ~256-576 threads per CTA with the best lane efficiency, subject to shared memory
+    // planes per CTA: best lane efficiency with <= 288 threads (3 CTAs/SM at <= 72 registers);
+    // wider CTAs only if a narrow one would idle more than 15 % of its lanes
     int best = 1;
     double best_eff = 0.0;
-    for (int G = 1; G <= 8; ++G) {
-      const int thr = round_threads(G * p->W);
-      if (thr > 576 && G > 1) break;
-      if (thr > 1024) break;
+    for (int limit : {288, 576}) {
+      for (int G = 1; G <= 16; ++G) {
+        const int thr = round_threads(G * p->W);
+        if (thr > limit) break;
+        const size_t sm = fwd ? fwd_smem_bytes(p, G) : inv_smem_bytes(p, G);
+        if (sm > kMaxSmem) break;
+        const double eff = (double)(G * p->W) / thr;
+        if (eff > best_eff + 0.02) { best_eff = eff; best = G; }
+      }
+      if (best_eff >= 0.85) break;
+    }
+    const char* env = std::getenv(fwd ? "FNO_G_FWD" : "FNO_G_INV");  // tuning override
+    if (env != nullptr && std::atoi(env) > 0) {
+      const int G = std::atoi(env);
       const size_t sm = fwd ? fwd_smem_bytes(p, G) : inv_smem_bytes(p, G);
-      if (sm > kMaxSmem) break;
-      const double eff = (double)(G * p->W) / thr;
-      if (eff > best_eff + 0.02) { best_eff = eff; best = G; }
+      if (round_threads(G * p->W) <= 1024 && sm <= kMaxSmem) best = G;
     }
     return best;
   };
