@@ -115,6 +115,47 @@ size_t fno_pointwise_wgrad_workspace_bytes(int B, int Co, int Ci, long N);
 int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B,
                         int Co, int Ci, long N, fno_stream_t stream);
 
+/* ---- lift: per-sample normalisation + fc0, written into the trunk layout ------ */
+/* Trunk layout of an activation: h[b, c, r, w], r < R_out rows of pitch Wp floats per channel
+ * plane; valid region r < R_in, w < W_in, zero elsewhere.  2-D: (R_in, W_in) = (X, Y), padded by
+ * F.pad(x, [0, p, 0, p]) (fno/fno.py:159); 3-D: rows = (X, Y) flattened, W_in = Z, only the last
+ * axis padded (fno/fno.py:360).
+ *
+ * torch.std_mean(x, dim=(1,2,3[,4])) + 1e-7 (fno/fno.py:140-142, :343-345):
+ *   x [B, entries, V] f32 (entries = pixels * time steps) -> stats [B, 2, V] = (mean, std + 1e-7)
+ *   work: fno_lift_stats_workspace_bytes(B, V) bytes                                             */
+size_t fno_lift_stats_workspace_bytes(int B, int V);
+int fno_lift_stats(const float* x, float* stats, void* work, int B, long entries, int V,
+                   fno_stream_t stream);
+/* normalise, reshape to [.., T*V], cat grid, fc0, permute to channel-first, zero pad
+ * (fno/fno.py:143-159, :346-360):
+ *   x [B, R_in*W_in, T, V], grid [B, R_in*W_in, G], W0 [C, T*V+G], b0 [C] -> h [B, C, R_out, Wp]   */
+int fno_lift_fwd(const float* x, const float* grid, const float* stats, const float* W0,
+                 const float* b0, float* h, int B, int R_in, int W_in, int R_out, int Wp, int T,
+                 int V, int G, int C, fno_stream_t stream);
+/* autograd backward of the above w.r.t. fc0: gW0 [C, T*V+G], gb0 [C] from dh [B, C, R_out, Wp]
+ * (the model input and the statistics carry no gradient, fno/fno.py:140).                          */
+size_t fno_lift_bwd_workspace_bytes(int T, int V, int G, int C);
+int fno_lift_bwd(const float* x, const float* grid, const float* stats, const float* dh, float* gW0,
+                 float* gb0, void* work, int B, int R_in, int W_in, int R_out, int Wp, int T, int V,
+                 int G, int C, fno_stream_t stream);
+
+/* ---- projection head: unpad, fc1, exact GELU, fc2, de-normalise ---------------- */
+/* fno/fno.py:180-187, :381-389.  h [B, C, R_out, Wp] (trunk layout, read in place), W1 [HID, C],
+ * b1 [HID], W2 [V, HID], b2 [V], stats as above -> out [B, R_in*W_in, V]
+ *   out = (W2 gelu(W1 h + b1) + b2) * std + mean.   The hidden layer never reaches memory.        */
+int fno_head_fwd(const float* h, const float* W1, const float* b1, const float* W2, const float* b2,
+                 const float* stats, float* out, int B, int R_in, int W_in, int R_out, int Wp, int C,
+                 int HID, int V, fno_stream_t stream);
+/* backward: dout [B, R_in*W_in, V] -> dh [B, C, R_out, Wp] (zero in the padding), gW1, gb1, gW2,
+ * gb2; the hidden layer is recomputed.  HID must be a multiple of 8, <= 128 (the reference
+ * hard-codes 128).  work: fno_head_bwd_workspace_bytes(C, HID, V) bytes.                           */
+size_t fno_head_bwd_workspace_bytes(int C, int HID, int V);
+int fno_head_bwd(const float* h, const float* dout, const float* W1, const float* b1, const float* W2,
+                 const float* stats, float* dh, float* gW1, float* gb1, float* gW2, float* gb2,
+                 void* work, int B, int R_in, int W_in, int R_out, int Wp, int C, int HID, int V,
+                 fno_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,4 +62,34 @@ __device__ __forceinline__ float gelu_exact_grad(float s) {
   return fmaf(s, pdf, cdf);
 }
 
+
+// Exact-erf GELU and its derivative through the Abramowitz-Stegun 7.1.26 rational form of erfc,
+// which shares exp(-s^2/2) with the Gaussian pdf of the derivative.  Absolute error of the cdf
+// < 6e-7 in fp32 (tests/test_kernels_gpu.py::test_gelu_fast bounds it), far inside the 1e-5
+// parity budget; ~15 instructions instead of ~40 for erff + expf.  The negative tail is computed
+// without cancellation (cdf = q), the positive one as 1 - q.
+__device__ __forceinline__ void gelu_fast_both(float s, float& g, float& gp) {
+  const float az = fabsf(s) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, az, 1.0f));
+  const float e = __expf(-az * az);
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float q = 0.5f * poly * t * e;            // 0.5 * erfc(|z|)
+  const float cdf = (s >= 0.0f) ? 1.0f - q : q;
+  g = s * cdf;
+  gp = fmaf(s * 0.39894228040143267794f, e, cdf);
+}
+__device__ __forceinline__ float gelu_fast(float s) {
+  float g, gp;
+  gelu_fast_both(s, g, gp);
+  return g;
+}
+__device__ __forceinline__ float gelu_fast_grad(float s) {
+  float g, gp;
+  gelu_fast_both(s, g, gp);
+  return gp;
+}
+
 }  // namespace fno

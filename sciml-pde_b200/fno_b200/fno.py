@@ -3,14 +3,14 @@
 Constructor kwargs, submodule names, parameter shapes/dtypes, RNG consumption order and
 ``forward(x, grid)`` semantics follow the reference exactly (state_dict keys: 22 for FNO2d, 50 for
 FNO3d including the never-called ``bn0..3``).  The four Fourier layers -- spectral convolution,
-1x1-conv bypass, add, exact GELU -- run as fused sm_100a kernel sequences (fno_b200.ops); the
-lift (fc0), projection head (fc1/fc2) and the normalisation around them are torch library calls
-("next").
+1x1-conv bypass, add, exact GELU -- run as fused sm_100a kernel sequences (fno_b200.ops), and so
+do the lift (statistics, normalisation, grid concat, fc0, permute, pad: one kernel writing the
+trunk layout) and the projection head (unpad, fc1, GELU, fc2, de-normalisation: one kernel, the
+128-wide hidden layer never reaches memory) -- SURVEY.md 8f rows f1/f2.
 """
 from __future__ import annotations
 
 import torch
-import torch.nn.functional as F
 from torch import nn
 
 from . import lib, ops
@@ -23,6 +23,18 @@ def _trunk(model, x: torch.Tensor) -> torch.Tensor:
         w = getattr(model, f"w{layer}")
         x = ops.fourier_layer(x, w.weight, w.bias, layer < 3, conv._weights())
     return x
+
+
+def _lift(model, x, grid):
+    """std_mean -> normalise -> [x_tv, grid] -> fc0 -> channel-first -> zero pad, one kernel writing
+    the trunk layout (fno.py:140-159 / :343-360).  Returns (h, stats [B, 2, V], geometry)."""
+    return ops.lift(x, grid, model.fc0.weight, model.fc0.bias, model.padding)
+
+
+def _project(model, h, fc2, stats, geo):
+    """unpad -> fc1 -> GELU -> fc2 -> de-normalise -> unsqueeze(-2) (fno.py:180-188 / :381-390)."""
+    out = ops.head(h, model.fc1.weight, model.fc1.bias, fc2.weight, fc2.bias, stats, geo)
+    return out.unsqueeze(-2)
 
 
 def _check_cuda(model, x):
@@ -50,26 +62,11 @@ class FNO2d(nn.Module):
     def _make_heads(self, num_channels):
         self.fc2 = nn.Linear(128, num_channels)
 
-    def _lift(self, x, grid):
-        with torch.no_grad():
-            std, mean = torch.std_mean(x, dim=(1, 2, 3), keepdim=True)
-            std = std + 1e-7
-        x = (x - mean) / std
-        feat = torch.cat((x.reshape(*x.shape[:-2], -1), grid), dim=-1)
-        h = self.fc0(feat).permute(0, 3, 1, 2)
-        return F.pad(h, [0, self.padding, 0, self.padding]), std, mean
-
-    def _project(self, h, fc2, std, mean):
-        h = h[..., : -self.padding, : -self.padding].permute(0, 2, 3, 1)
-        out = fc2(F.gelu(self.fc1(h)))
-        out = out * std.squeeze(-2) + mean.squeeze(-2)
-        return out.unsqueeze(-2)
-
     def forward(self, x, grid):
         _check_cuda(self, x)
-        h, std, mean = self._lift(x, grid)
+        h, stats, geo = _lift(self, x, grid)
         h = _trunk(self, h)
-        return self._project(h, self.fc2, std, mean)
+        return _project(self, h, self.fc2, stats, geo)
 
 
 class FNO3d(nn.Module):
@@ -94,23 +91,8 @@ class FNO3d(nn.Module):
     def _make_heads(self, num_channels):
         self.fc2 = nn.Linear(128, num_channels)
 
-    def _lift(self, x, grid):
-        with torch.no_grad():
-            std, mean = torch.std_mean(x, dim=(1, 2, 3, 4), keepdim=True)
-            std = std + 1e-7
-        x = (x - mean) / std
-        feat = torch.cat((x.reshape(*x.shape[:-2], -1), grid), dim=-1)
-        h = self.fc0(feat).permute(0, 4, 1, 2, 3)
-        return F.pad(h, [0, self.padding]), std, mean
-
-    def _project(self, h, fc2, std, mean):
-        h = h[..., : -self.padding].permute(0, 2, 3, 4, 1)
-        out = fc2(F.gelu(self.fc1(h)))
-        out = out * std.squeeze(-2) + mean.squeeze(-2)
-        return out.unsqueeze(-2)
-
     def forward(self, x, grid):
         _check_cuda(self, x)
-        h, std, mean = self._lift(x, grid)
+        h, stats, geo = _lift(self, x, grid)
         h = _trunk(self, h)
-        return self._project(h, self.fc2, std, mean)
+        return _project(self, h, self.fc2, stats, geo)

@@ -53,8 +53,8 @@ class FNO3d(_base.FNO3d):
 def _two_head_forward(model, x, grid, x_aux, grid_aux):
     _base._check_cuda(model, x)
     nb = x.shape[0]
-    h, std, mean = model._lift(torch.cat((x, x_aux), dim=0), torch.cat((grid, grid_aux), dim=0))
+    h, stats, geo = _base._lift(model, torch.cat((x, x_aux), dim=0), torch.cat((grid, grid_aux), dim=0))
     h = _base._trunk(model, h)
-    out_p = model._project(h[:nb], model.fc2_primary, std[:nb], mean[:nb])
-    out_a = model._project(h[nb:], model.fc2_auxiliary, std[nb:], mean[nb:])
+    out_p = _base._project(model, h[:nb], model.fc2_primary, stats[:nb].contiguous(), geo)
+    out_a = _base._project(model, h[nb:], model.fc2_auxiliary, stats[nb:].contiguous(), geo)
     return out_p, out_a

@@ -63,6 +63,14 @@ def load():
             "fno_pointwise_fwd": (i, [vp, vp, vp, vp, i, i, i, l, i, vp]),
             "fno_pointwise_wgrad_workspace_bytes": (C.c_size_t, [i, i, i, l]),
             "fno_pointwise_wgrad": (i, [vp, vp, vp, vp, vp, i, i, i, l, vp]),
+            "fno_lift_stats_workspace_bytes": (C.c_size_t, [i, i]),
+            "fno_lift_stats": (i, [vp, vp, vp, i, l, i, vp]),
+            "fno_lift_fwd": (i, [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+            "fno_lift_bwd_workspace_bytes": (C.c_size_t, [i, i, i, i]),
+            "fno_lift_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
+            "fno_head_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
+            "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
+            "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -78,6 +86,8 @@ EXPORTED_SYMBOLS = (
     "fno_sc2d_fwd_transform", "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
+    "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
+    "fno_lift_bwd", "fno_head_fwd", "fno_head_bwd_workspace_bytes", "fno_head_bwd",
 )
 
 
@@ -310,3 +320,93 @@ def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bia
                                  _stream())
     _check(rc, "fno_pointwise_wgrad")
     return gw, gb
+
+
+# ---------------------------------------------------------------------------------------------
+# lift / projection head (trunk layout h[B, C, R_out, Wp], see include/fno_sm100.h)
+# ---------------------------------------------------------------------------------------------
+class TrunkGeo:
+    """Geometry of the channel-first padded trunk activation for inputs [B, *spatial, ...]."""
+
+    def __init__(self, spatial: Sequence[int], padding: int):
+        self.spatial = tuple(int(s) for s in spatial)
+        self.padding = int(padding)
+        if len(self.spatial) == 2:      # F.pad(x, [0, p, 0, p]): both axes (fno.py:159)
+            self.R_in, self.W_in = self.spatial
+            self.R_out, self.Wp = self.R_in + padding, self.W_in + padding
+            self.padded = (self.R_out, self.Wp)
+        elif len(self.spatial) == 3:    # F.pad(x, [0, p]): last axis only (fno.py:360)
+            self.R_in, self.W_in = self.spatial[0] * self.spatial[1], self.spatial[2]
+            self.R_out, self.Wp = self.R_in, self.W_in + padding
+            self.padded = (self.spatial[0], self.spatial[1], self.Wp)
+        else:
+            raise FnoError("only 2-D and 3-D models exist in the reference")
+        self.npix = self.R_in * self.W_in
+
+    @property
+    def ints(self):
+        return self.R_in, self.W_in, self.R_out, self.Wp
+
+
+def lift_stats(x: torch.Tensor) -> torch.Tensor:
+    """x [B, *spatial, T, V] -> [B, 2, V] (mean, std + 1e-7) over everything but batch and variable."""
+    _require(x, torch.float32, "x")
+    B, V = x.shape[0], x.shape[-1]
+    entries = x.numel() // (B * V)
+    lib = load()
+    work = torch.empty(lib.fno_lift_stats_workspace_bytes(B, V) // 4, dtype=torch.float32, device=x.device)
+    stats = torch.empty((B, 2, V), dtype=torch.float32, device=x.device)
+    _check(lib.fno_lift_stats(x.data_ptr(), stats.data_ptr(), work.data_ptr(), B, entries, V, _stream()),
+           "fno_lift_stats")
+    return stats
+
+
+def lift_fwd(geo: TrunkGeo, x, grid, stats, W0, b0) -> torch.Tensor:
+    for t, n in ((x, "x"), (grid, "grid"), (stats, "stats"), (W0, "fc0.weight"), (b0, "fc0.bias")):
+        _require(t, torch.float32, n)
+    B, T, V, G, C = x.shape[0], x.shape[-2], x.shape[-1], grid.shape[-1], W0.shape[0]
+    if W0.shape[1] != T * V + G:
+        raise FnoError(f"fc0.weight has {W0.shape[1]} inputs, expected {T * V + G}")
+    h = torch.empty((B, C) + geo.padded, dtype=torch.float32, device=x.device)
+    _check(load().fno_lift_fwd(x.data_ptr(), grid.data_ptr(), stats.data_ptr(), W0.data_ptr(), b0.data_ptr(),
+                               h.data_ptr(), B, *geo.ints, T, V, G, C, _stream()), "fno_lift_fwd")
+    return h
+
+
+def lift_bwd(geo: TrunkGeo, x, grid, stats, dh, W0_shape):
+    _require(dh, torch.float32, "dh")
+    B, T, V, G, C = x.shape[0], x.shape[-2], x.shape[-1], grid.shape[-1], W0_shape[0]
+    lib = load()
+    work = torch.empty(lib.fno_lift_bwd_workspace_bytes(T, V, G, C) // 4, dtype=torch.float32, device=x.device)
+    gW0 = torch.empty(tuple(W0_shape), dtype=torch.float32, device=x.device)
+    gb0 = torch.empty(C, dtype=torch.float32, device=x.device)
+    _check(lib.fno_lift_bwd(x.data_ptr(), grid.data_ptr(), stats.data_ptr(), dh.data_ptr(), gW0.data_ptr(),
+                            gb0.data_ptr(), work.data_ptr(), B, *geo.ints, T, V, G, C, _stream()), "fno_lift_bwd")
+    return gW0, gb0
+
+
+def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
+    for t, n in ((h, "h"), (W1, "fc1.weight"), (b1, "fc1.bias"), (W2, "fc2.weight"), (b2, "fc2.bias"),
+                 (stats, "stats")):
+        _require(t, torch.float32, n)
+    B, C, HID, V = h.shape[0], h.shape[1], W1.shape[0], W2.shape[0]
+    if tuple(h.shape[2:]) != geo.padded or W1.shape[1] != C or W2.shape[1] != HID:
+        raise FnoError(f"head: inconsistent shapes h {tuple(h.shape)}, fc1 {tuple(W1.shape)}, fc2 {tuple(W2.shape)}")
+    out = torch.empty((B,) + geo.spatial + (V,), dtype=torch.float32, device=h.device)
+    _check(load().fno_head_fwd(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                               stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()), "fno_head_fwd")
+    return out
+
+
+def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
+    _require(dout, torch.float32, "dout")
+    B, C, HID, V = h.shape[0], h.shape[1], W1.shape[0], W2.shape[0]
+    lib = load()
+    work = torch.empty(lib.fno_head_bwd_workspace_bytes(C, HID, V) // 4, dtype=torch.float32, device=h.device)
+    dh = torch.empty_like(h)
+    gW1, gb1 = torch.empty_like(W1), torch.empty(HID, dtype=torch.float32, device=h.device)
+    gW2, gb2 = torch.empty_like(W2), torch.empty(V, dtype=torch.float32, device=h.device)
+    _check(lib.fno_head_bwd(h.data_ptr(), dout.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
+                            stats.data_ptr(), dh.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(),
+                            gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()), "fno_head_bwd")
+    return dh, gW1, gb1, gW2, gb2

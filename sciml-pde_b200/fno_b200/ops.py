@@ -117,3 +117,59 @@ class FourierLayerFn(torch.autograd.Function):
 
 def fourier_layer(a, wl, bl, apply_gelu: bool, weights: Sequence[torch.Tensor]) -> torch.Tensor:
     return FourierLayerFn.apply(a, wl, bl, apply_gelu, *weights)
+
+
+class LiftFn(torch.autograd.Function):
+    """h = pad(permute(fc0(cat(normalise(x), grid))))  -- fno/fno.py:140-159, :343-360.
+
+    One kernel writes the trunk layout directly; backward is the fc0 weight/bias gradient
+    (x, grid and the no_grad statistics receive none, as in the reference)."""
+
+    @staticmethod
+    def forward(ctx, x, grid, stats, W0, b0, geo):
+        x, grid = x.contiguous(), grid.contiguous()
+        W0, b0 = W0.contiguous(), b0.contiguous()
+        h = lib.lift_fwd(geo, x, grid, stats, W0, b0)
+        ctx.geo = geo
+        ctx.w_shape = W0.shape
+        ctx.save_for_backward(x, grid, stats)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        x, grid, stats = ctx.saved_tensors
+        gW0, gb0 = lib.lift_bwd(ctx.geo, x, grid, stats, dh.contiguous(), ctx.w_shape)
+        return None, None, None, gW0, gb0, None
+
+
+class HeadFn(torch.autograd.Function):
+    """out = fc2(gelu(fc1(unpad(h)))) * std + mean  -- fno/fno.py:180-187, :381-389.
+
+    Saves only h: the 128-wide hidden layer is recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, h, W1, b1, W2, b2, stats, geo):
+        h = h.contiguous()
+        W1, b1, W2, b2 = W1.contiguous(), b1.contiguous(), W2.contiguous(), b2.contiguous()
+        out = lib.head_fwd(geo, h, W1, b1, W2, b2, stats)
+        ctx.geo = geo
+        ctx.save_for_backward(h, W1, b1, W2, stats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, W1, b1, W2, stats = ctx.saved_tensors
+        dh, gW1, gb1, gW2, gb2 = lib.head_bwd(ctx.geo, h, dout.contiguous(), W1, b1, W2, stats)
+        return dh, gW1, gb1, gW2, gb2, None, None
+
+
+def lift(x, grid, W0, b0, padding: int):
+    """Returns (h in trunk layout, stats [B, 2, V], geometry)."""
+    geo = lib.TrunkGeo(x.shape[1:-2], padding)
+    with torch.no_grad():
+        stats = lib.lift_stats(x.contiguous())
+    return LiftFn.apply(x, grid, stats, W0, b0, geo), stats, geo
+
+
+def head(h, W1, b1, W2, b2, stats, geo):
+    return HeadFn.apply(h, W1, b1, W2, b2, stats, geo)

@@ -236,3 +236,117 @@ def test_errors_are_loud(lib):
         lib.fwd_transform(plan, torch.zeros(1, 1, 8, 9, device="cuda"))
     with pytest.raises(lib.FnoError):
         lib.fwd_transform(plan, torch.zeros(1, 1, 8, 8, device="cuda", dtype=torch.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# lift (statistics + normalise + fc0 + pad) and projection head (fc1 + GELU + fc2 + de-normalise)
+# checked against the fp64 oracle port (oracle/fno_port.py: _normalise / _lift / _project)
+# ---------------------------------------------------------------------------------------------
+LIFT_CASES = [
+    # spatial, T, V, C          (2-D: pad 2 on both axes; 3-D: pad 6 on the last axis)
+    ((9, 7), 3, 2, 8),
+    ((16, 16), 10, 2, 20),
+    ((5, 66), 2, 3, 6),          # W_in > one 64-pixel tile, width not a multiple of 4
+    ((4, 5, 6), 2, 3, 6),
+    ((6, 6, 10), 3, 5, 20),      # V = 5 (cfg 4 channel count)
+    ((12, 10), 2, 1, 32),
+]
+
+
+def _lift_inputs(spatial, T, V, C, seed):
+    g = torch.Generator().manual_seed(seed)
+    B, nd = 3, len(spatial)
+    x = torch.randn((B,) + spatial + (T, V), generator=g) * torch.tensor([0.5, 3.0, 0.01, 1.0, 2.0][:V]) \
+        + torch.tensor([10.0, -2.0, 1.0, 0.0, 100.0][:V])       # |mean| >> std in some variables
+    grid = torch.rand((B,) + spatial + (nd,), generator=g)
+    W0 = torch.randn(C, T * V + nd, generator=g) / 4
+    b0 = torch.randn(C, generator=g)
+    return x, grid, W0, b0
+
+
+@pytest.mark.parametrize("spatial,T,V,C", LIFT_CASES)
+def test_lift_stats(lib, spatial, T, V, C):
+    x, _, _, _ = _lift_inputs(spatial, T, V, C, 1)
+    nd = len(spatial)
+    stats = lib.lift_stats(x.cuda()).cpu().double()
+    std, mean = torch.std_mean(x.double(), dim=tuple(range(1, nd + 2)))
+    assert float((stats[:, 0] - mean).abs().max() / mean.abs().max()) < 1e-6
+    assert float(((stats[:, 1] - (std + 1e-7)) / std).abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("spatial,T,V,C", LIFT_CASES)
+def test_lift_forward_backward(lib, spatial, T, V, C):
+    from fno_b200 import ops
+    from oracle import fno_port as P
+
+    x, grid, W0, b0 = _lift_inputs(spatial, T, V, C, 2)
+    nd = len(spatial)
+    pad = 2 if nd == 2 else 6
+    # oracle, fp64 autograd
+    p = {"fc0.weight": W0.double().requires_grad_(), "fc0.bias": b0.double().requires_grad_()}
+    xn, _, _ = P._normalise(x.double(), nd)
+    h_ref = P._lift(p, xn, grid.double(), nd)
+    gh = torch.randn(h_ref.shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
+    h_ref.backward(gh)
+    # CUDA
+    W0c, b0c = W0.cuda().requires_grad_(), b0.cuda().requires_grad_()
+    h, stats, geo = ops.lift(x.cuda(), grid.cuda(), W0c, b0c, pad)
+    assert tuple(h.shape) == tuple(h_ref.shape)
+    assert O.rel_err(h.detach().cpu().numpy(), h_ref.detach().numpy()) < TOL
+    h.backward(gh.float().cuda())
+    assert O.rel_err(W0c.grad.cpu().numpy(), p["fc0.weight"].grad.numpy()) < TOL
+    assert O.rel_err(b0c.grad.cpu().numpy(), p["fc0.bias"].grad.numpy()) < TOL
+
+
+HEAD_CASES = [
+    # spatial, C, V, B
+    ((9, 7), 8, 2, 2),
+    ((16, 16), 20, 2, 3),
+    ((5, 66), 6, 3, 2),
+    ((3, 130), 20, 1, 1),
+    ((4, 5, 6), 6, 3, 2),
+    ((6, 6, 10), 20, 5, 2),
+    ((12, 10), 32, 4, 2),
+    ((8, 8), 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("spatial,C,V,B", HEAD_CASES)
+def test_head_forward_backward(lib, spatial, C, V, B):
+    from fno_b200 import ops
+    from oracle import fno_port as P
+
+    g = torch.Generator().manual_seed(5)
+    nd = len(spatial)
+    pad = 2 if nd == 2 else 6
+    geo = lib.TrunkGeo(spatial, pad)
+    h = torch.randn((B, C) + geo.padded, generator=g) * 1.5
+    W1 = torch.randn(128, C, generator=g) / C ** 0.5
+    b1 = torch.randn(128, generator=g) * 0.3
+    W2 = torch.randn(V, 128, generator=g) / 11
+    b2 = torch.randn(V, generator=g)
+    mean = torch.randn(B, V, generator=g)
+    std = torch.rand(B, V, generator=g) + 0.5
+    stats = torch.stack((mean, std), dim=1).contiguous()
+    # oracle, fp64 autograd
+    p = {"fc1.weight": W1.double().requires_grad_(), "fc1.bias": b1.double().requires_grad_(),
+         "fc2.weight": W2.double().requires_grad_(), "fc2.bias": b2.double().requires_grad_()}
+    h64 = h.double().requires_grad_()
+    bshape = (B,) + (1,) * nd + (V,)
+    out_ref = P._project(p, h64, nd, "fc2") * std.double().view(bshape) + mean.double().view(bshape)
+    gout = torch.randn(out_ref.shape, generator=g, dtype=torch.float64)
+    out_ref.backward(gout)
+    # CUDA
+    hc = h.cuda().requires_grad_()
+    leaves = [t.cuda().requires_grad_() for t in (W1, b1, W2, b2)]
+    out = ops.head(hc, *leaves, stats.cuda(), geo)
+    assert tuple(out.shape) == tuple(out_ref.shape)
+    assert O.rel_err(out.detach().cpu().numpy(), out_ref.detach().numpy()) < TOL
+    out.backward(gout.float().cuda())
+    assert O.rel_err(hc.grad.cpu().numpy(), h64.grad.numpy()) < TOL
+    # the padding of dh must be exactly zero (F.pad backward drops it; layer 3 reads all of dh)
+    pad_mask = torch.ones_like(h, dtype=torch.bool)
+    pad_mask[(Ellipsis,) + tuple(slice(0, s) for s in (spatial if nd == 2 else (spatial[0], spatial[1], spatial[2])))] = False
+    assert float(hc.grad.cpu()[pad_mask].abs().max()) == 0.0
+    for t, name in zip(leaves, ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")):
+        assert O.rel_err(t.grad.cpu().numpy(), p[name].grad.numpy()) < TOL, name
