@@ -195,15 +195,30 @@ lift_fwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
 // lift backward: gW0[c][f] = sum_{b,p} dh[b,c,p] feat[b,p,f],  gb0[c] = sum dh
 // persistent CTAs over 64-pixel tiles; thread item = (c, 4 consecutive f) with lanes over items
 // ------------------------------------------------------------------------------------------
-constexpr int TILE = 64;          // pixels per tile
+constexpr int TILE = 64;          // pixels per tile: a 64-wide piece of one row
 constexpr int TP = TILE + 4;      // shared-memory pitch (floats): rows 16-B aligned, bank-skewed
 constexpr int LB_THREADS = 256;
 constexpr int LB_ITEMS = 4;       // (c, f-quad) items per thread
+constexpr int LB_CTAS = 148 * 3;
 
-__global__ void __launch_bounds__(LB_THREADS)
+// tile -> (sample, row, first column); tiles never straddle rows, so a pixel's offset in the padded
+// layout is r * Wp + w with no division per element
+struct TileMap {
+  int tiles_per_row;
+  int total;
+};
+__device__ __forceinline__ void decode_tile(const TileMap& tm, const PixGeo& g, int tile, int& b, int& r, int& w0) {
+  const int wc = tile % tm.tiles_per_row;
+  const int t = tile / tm.tiles_per_row;
+  r = t % g.R_in;
+  b = t / g.R_in;
+  w0 = wc * TILE;
+}
+
+__global__ void __launch_bounds__(LB_THREADS, 3)
 lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, const float* __restrict__ stats,
-                const float* __restrict__ dh, float* __restrict__ part, PixGeo g, int T, int V, int G, int C,
-                int B, long tiles_per_sample, long total_tiles) {
+                const float* __restrict__ dh, float* __restrict__ part, PixGeo g, TileMap tm, int T, int V, int G,
+                int C, int KSPL) {
   extern __shared__ __align__(16) float sm[];
   const int F1 = T * V, F = F1 + G;
   const int FQ = (F + 1 + 3) / 4;            // feature quads incl. the bias "feature" (= 1)
@@ -217,33 +232,45 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
 #pragma unroll
     for (int q = 0; q < 4; ++q) acc[k][q] = 0.f;
 
-  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_per_sample);
-    const long p0 = (tile - (long)b * tiles_per_sample) * TILE;
+  const int k = threadIdx.x & (TILE - 1);     // pixel of the tile staged by this thread
+  const int pt = threadIdx.x / TILE;          // which quarter of the channels / features it stages
+  const int FCH = FR / 4;
+  // compute-phase ownership
+  const int slot = (KSPL == 2) ? (threadIdx.x & 127) : threadIdx.x;
+  const int ks = (KSPL == 2) ? (threadIdx.x >> 7) : 0;
+  const int q0 = ks * (TILE / 4 / KSPL), q1 = q0 + TILE / 4 / KSPL;
+
+  for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x) {
+    int b, r, w0;
+    decode_tile(tm, g, tile, b, r, w0);
+    const int w = w0 + k;
+    const bool valid = w < g.W_in;
     const float* __restrict__ mean = stats + (size_t)b * 2 * V;
     const float* __restrict__ sd = mean + V;
     __syncthreads();
-    for (int i = threadIdx.x; i < C * TILE; i += LB_THREADS) {
-      const int c = i / TILE, k = i - c * TILE;
-      const long p = p0 + k;
-      dhs[c * TP + k] = (p < g.npix) ? __ldg(dh + ((size_t)b * C + c) * g.plane + pix_offset(g, p)) : 0.f;
-    }
-    for (int i = threadIdx.x; i < FR * TILE; i += LB_THREADS) {
-      // feature-fastest over the global read (x is pixel-major), transposed into fs[f][k]
-      const int k = i / FR, f = i - k * FR;
-      const long p = p0 + k;
-      float v = 0.f;
-      if (p < g.npix) {
-        if (f < F1) v = (__ldg(x + ((size_t)b * g.npix + p) * F1 + f) - __ldg(mean + f % V)) * (1.0f / __ldg(sd + f % V));
-        else if (f < F) v = __ldg(grid + ((size_t)b * g.npix + p) * G + (f - F1));
-        else if (f == F) v = 1.f;
+    {
+      const float* __restrict__ dp = dh + (size_t)b * C * g.plane + (size_t)r * g.Wp + w;
+      for (int c = pt; c < C; c += LB_THREADS / TILE) dhs[c * TP + k] = valid ? __ldg(dp + (size_t)c * g.plane) : 0.f;
+      const size_t pidx = (size_t)b * g.npix + (size_t)r * g.W_in + w;
+      const float* __restrict__ xp = x + pidx * F1;
+      const float* __restrict__ gp = grid + pidx * G;
+      const int f0 = pt * FCH;
+      int vi = f0 % V;
+      for (int f = f0; f < f0 + FCH; ++f) {
+        float v = 0.f;
+        if (valid) {
+          if (f < F1) v = (__ldg(xp + f) - __ldg(mean + vi)) * (1.0f / __ldg(sd + vi));
+          else if (f < F) v = __ldg(gp + (f - F1));
+          else if (f == F) v = 1.f;
+        }
+        fs[f * TP + k] = v;
+        if (++vi == V) vi = 0;
       }
-      fs[f * TP + k] = v;
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < LB_ITEMS; ++k) {
-      const int item = threadIdx.x + k * LB_THREADS;
+    for (int kk = 0; kk < LB_ITEMS; ++kk) {
+      const int item = slot + kk * LB_THREADS;
       if (item >= nitems) break;
       const int c = item / FQ, fq = item - c * FQ;
       const float4* d4 = reinterpret_cast<const float4*>(dhs + c * TP);
@@ -252,25 +279,27 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
       const float4* f2 = reinterpret_cast<const float4*>(fs + (4 * fq + 2) * TP);
       const float4* f3 = reinterpret_cast<const float4*>(fs + (4 * fq + 3) * TP);
 #pragma unroll 4
-      for (int q = 0; q < TILE / 4; ++q) {
+      for (int q = q0; q < q1; ++q) {
         const float4 d = d4[q];
         const float4 a0 = f0[q], a1 = f1[q], a2 = f2[q], a3 = f3[q];
 #define FNO_DOT4(P, U, Vv) P = fmaf(U.x, Vv.x, P); P = fmaf(U.y, Vv.y, P); P = fmaf(U.z, Vv.z, P); P = fmaf(U.w, Vv.w, P);
-        FNO_DOT4(acc[k][0], d, a0) FNO_DOT4(acc[k][1], d, a1) FNO_DOT4(acc[k][2], d, a2) FNO_DOT4(acc[k][3], d, a3)
+        FNO_DOT4(acc[kk][0], d, a0) FNO_DOT4(acc[kk][1], d, a1) FNO_DOT4(acc[kk][2], d, a2) FNO_DOT4(acc[kk][3], d, a3)
 #undef FNO_DOT4
       }
+      if (KSPL == 2) break;                   // one item per thread when the pixel range is split
     }
   }
-  // part[cta][c][F + 1]
-  float* __restrict__ pp = part + (size_t)blockIdx.x * C * (F + 1);
+  // part[cta * KSPL + ks][c][F + 1]
+  float* __restrict__ pp = part + ((size_t)blockIdx.x * KSPL + ks) * C * (F + 1);
 #pragma unroll
-  for (int k = 0; k < LB_ITEMS; ++k) {
-    const int item = threadIdx.x + k * LB_THREADS;
+  for (int kk = 0; kk < LB_ITEMS; ++kk) {
+    const int item = slot + kk * LB_THREADS;
     if (item >= nitems) break;
     const int c = item / FQ, fq = item - c * FQ;
 #pragma unroll
     for (int q = 0; q < 4; ++q)
-      if (4 * fq + q <= F) pp[(size_t)c * (F + 1) + 4 * fq + q] = acc[k][q];
+      if (4 * fq + q <= F) pp[(size_t)c * (F + 1) + 4 * fq + q] = acc[kk][q];
+    if (KSPL == 2) break;
   }
 }
 
@@ -403,8 +432,7 @@ template <int CP, int VP>
 __global__ void __launch_bounds__(HB_THREADS, (CP <= 20 ? 2 : 1))
 head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, const float* __restrict__ W1,
                 const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ stats,
-                float* __restrict__ dh, float* __restrict__ part, PixGeo g, int C, int HID, int V, int B,
-                long tiles_per_sample, long total_tiles) {
+                float* __restrict__ dh, float* __restrict__ part, PixGeo g, TileMap tm, int C, int HID, int V) {
   constexpr int TC = CP / 4;                 // channels per phase-B1 thread
   extern __shared__ __align__(16) float sm[];
   float* W1s = sm;                           // [HID][CP]
@@ -443,24 +471,30 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
 #pragma unroll
   for (int v = 0; v < VP; ++v) aw2[v] = 0.f;
 
-  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int b = (int)(tile / tiles_per_sample);
-    const long p = (tile - (long)b * tiles_per_sample) * TILE + pix;
-    const bool valid = p < g.npix;
-    const long off = valid ? pix_offset(g, p) : 0;
+  // inputs of one tile for this thread's pixel: h[0..C), dout * std
+  float hv[CP], dv[VP];
+  auto load_tile = [&](int tile) {
+    int b, r, w0;
+    decode_tile(tm, g, tile, b, r, w0);
+    const int w = w0 + pix;
+    const bool valid = w < g.W_in;
+    const float* __restrict__ hp = h + (size_t)b * C * g.plane + (size_t)r * g.Wp + w;
+    const float* __restrict__ op = dout + ((size_t)b * g.npix + (size_t)r * g.W_in + w) * V;
     const float* __restrict__ sd = stats + (size_t)b * 2 * V + V;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) hv[c] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+#pragma unroll
+    for (int v = 0; v < VP; ++v) dv[v] = (valid && v < V) ? __ldg(op + v) * __ldg(sd + v) : 0.f;
+  };
+  if ((int)blockIdx.x < tm.total) load_tile(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x) {
     __syncthreads();   // previous tile's phase B done (also covers the weight staging on entry)
 
     // ---- phase A --------------------------------------------------------------------------
-    float hv[CP], dv[VP], dacc[CP];
+    float dacc[CP];
 #pragma unroll
-    for (int c = 0; c < CP; ++c) {
-      hv[c] = (valid && c < C) ? __ldg(h + ((size_t)b * C + c) * g.plane + off) : 0.f;
-      dacc[c] = 0.f;
-    }
-#pragma unroll
-    for (int v = 0; v < VP; ++v)
-      dv[v] = (valid && v < V) ? __ldg(dout + ((size_t)b * g.npix + p) * V + v) * __ldg(sd + v) : 0.f;
+    for (int c = 0; c < CP; ++c) dacc[c] = 0.f;
     if (jq == 0) {
 #pragma unroll
       for (int c = 0; c < CP; ++c) hs[c * TP + pix] = hv[c];
@@ -500,6 +534,8 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
     }
 #pragma unroll
     for (int c = 0; c < CP; ++c) dhs[(jq * CP + c) * TP + pix] = dacc[c];
+    // the next tile's inputs travel while phase B runs (hv / dv are dead until the next phase A)
+    if (tile + (int)gridDim.x < tm.total) load_tile(tile + gridDim.x);
     __syncthreads();
 
     // ---- phase B1: gW1 ------------------------------------------------------------------------
@@ -544,14 +580,18 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
       for (int k = 0; k < TILE; ++k) ab2 += dos[v * TP + k];
     }
     // dh[b, c, pixel] = sum of the four hidden-unit shares (all threads; coalesced over pixels)
-    for (int i = threadIdx.x; i < C * TILE; i += HB_THREADS) {
-      const int c = i / TILE, k = i - c * TILE;
-      const long pk = (tile - (long)b * tiles_per_sample) * TILE + k;
-      if (pk < g.npix) {
-        float s = 0.f;
+    {
+      int b, r, w0;
+      decode_tile(tm, g, tile, b, r, w0);
+      float* __restrict__ dp = dh + (size_t)b * C * g.plane + (size_t)r * g.Wp + w0;
+      for (int i = threadIdx.x; i < C * TILE; i += HB_THREADS) {
+        const int c = i / TILE, k = i - c * TILE;
+        if (w0 + k < g.W_in) {
+          float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < HB_JQ; ++q) s += dhs[(q * CP + c) * TP + k];
-        dh[((size_t)b * C + c) * g.plane + pix_offset(g, pk)] = s;
+          for (int q = 0; q < HB_JQ; ++q) s += dhs[(q * CP + c) * TP + k];
+          dp[(size_t)c * g.plane + k] = s;
+        }
       }
     }
   }
@@ -590,6 +630,14 @@ bool bad_geo(int B, int R_in, int W_in, int R_out, int Wp) {
 
 constexpr int PERSIST_CTAS = 148 * 2;
 
+TileMap make_tiles(const PixGeo& g, int B) {
+  TileMap tm;
+  tm.tiles_per_row = (g.W_in + TILE - 1) / TILE;
+  const long total = (long)B * g.R_in * tm.tiles_per_row;
+  tm.total = total < 0x7fffffffL ? (int)total : -1;
+  return tm;
+}
+
 template <int CP, int VP>
 size_t head_bwd_smem(int HID) {
   return sizeof(float) * ((size_t)HID * CP + (size_t)HID * VP + HID + 2ul * HID * TP + (size_t)CP * TP +
@@ -627,10 +675,10 @@ int launch_head_bwd(const float* h, const float* dout, const float* W1, const fl
     done.store(1);
   }
   if (smem > 227 * 1024) { set_error("head_bwd: hidden %d x width %d too large", HID, C); return FNO_E_ARG; }
-  const long tps = (g.npix + TILE - 1) / TILE;
-  const long total = tps * B;
-  const int ctas = (int)(total < PERSIST_CTAS ? total : PERSIST_CTAS);
-  k<<<ctas, HB_THREADS, smem, st>>>(h, dout, W1, b1, W2, stats, dh, part, g, C, HID, V, B, tps, total);
+  const TileMap tm = make_tiles(g, B);
+  if (tm.total <= 0) { set_error("head_bwd: too many pixel tiles"); return FNO_E_ARG; }
+  const int ctas = tm.total < PERSIST_CTAS ? tm.total : PERSIST_CTAS;
+  k<<<ctas, HB_THREADS, smem, st>>>(h, dout, W1, b1, W2, stats, dh, part, g, tm, C, HID, V);
   count_launch();
   int rc = check_launch("head_bwd_kernel");
   if (rc != FNO_OK) return rc;
@@ -743,7 +791,7 @@ extern "C" int fno_lift_fwd(const float* x, const float* grid, const float* stat
 
 extern "C" size_t fno_lift_bwd_workspace_bytes(int T, int V, int G, int C) {
   if (T < 1 || V < 1 || G < 0 || C < 1) return 0;
-  return sizeof(float) * (size_t)PERSIST_CTAS * C * (T * V + G + 1);
+  return sizeof(float) * 2ul * (size_t)LB_CTAS * C * (T * V + G + 1);
 }
 
 extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stats, const float* dh, float* gW0,
@@ -770,11 +818,12 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
     done.store(1);
   }
   if (smem > 160 * 1024) { set_error("fno_lift_bwd: tile does not fit shared memory"); return FNO_E_ARG; }
-  const long tps = (g.npix + TILE - 1) / TILE;
-  const long total = tps * B;
-  const int ctas = (int)(total < PERSIST_CTAS ? total : PERSIST_CTAS);
+  const TileMap tm = make_tiles(g, B);
+  if (tm.total <= 0) { set_error("fno_lift_bwd: too many pixel tiles"); return FNO_E_ARG; }
+  const int ctas = tm.total < LB_CTAS ? tm.total : LB_CTAS;
+  const int KSPL = (C * FQ <= 128) ? 2 : 1;      // split the tile's pixels over two half-CTAs when outputs are few
   float* part = static_cast<float*>(work);
-  lift_bwd_kernel<<<ctas, LB_THREADS, smem, st>>>(x, grid, stats, dh, part, g, T, V, G, C, B, tps, total);
+  lift_bwd_kernel<<<ctas, LB_THREADS, smem, st>>>(x, grid, stats, dh, part, g, tm, T, V, G, C, KSPL);
   count_launch();
   int rc = check_launch("lift_bwd_kernel");
   if (rc != FNO_OK) return rc;
@@ -783,7 +832,7 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
   segs.dst[0] = gW0; segs.n[0] = C * F; segs.row[0] = F; segs.stride[0] = F + 1; segs.col[0] = 0;
   segs.dst[1] = gb0; segs.n[1] = C;     segs.row[1] = 1; segs.stride[1] = F + 1; segs.col[1] = F;
   const int total_out = C * F + C;
-  partial_reduce_kernel<<<(total_out * 32 + 127) / 128, 128, 0, st>>>(part, ctas, C * (F + 1), segs);
+  partial_reduce_kernel<<<(total_out * 32 + 127) / 128, 128, 0, st>>>(part, ctas * KSPL, C * (F + 1), segs);
   count_launch();
   return check_launch("partial_reduce_kernel(lift)");
 }

@@ -71,6 +71,82 @@ pointwise_kernel(const float* __restrict__ in, const float* __restrict__ Wm, con
   }
 }
 
+// v2 of the forward / data-gradient product for even plane sizes: two adjacent pixels per thread
+// (64-bit coalesced accesses), every output channel of the CTA's tile in registers, and the input
+// channels fetched in bursts of PW_CH loads that are all issued before the first FMA consumes
+// them -- 16 resident warps per SM each with PW_CH x 8 bytes in flight cover the HBM latency that
+// the one-load-at-a-time loop above exposes (profiles/r1_b: 183 registers, 12 % occupancy).
+constexpr int PW_CH = 10;
+
+template <int OT, bool TRANSPOSE>
+__global__ void __launch_bounds__(256, 2)
+pointwise2_kernel(const float* __restrict__ in, const float* __restrict__ Wm, const float* __restrict__ bias,
+                  float* __restrict__ out, int Cin, int Cout, int Co, int Ci, long N2) {
+  extern __shared__ __align__(16) float ws[];  // [Cin][OT] weights, then [OT] bias
+  const int o0 = blockIdx.y * OT;
+  const int b = blockIdx.z;
+  for (int idx = threadIdx.x; idx < Cin * OT; idx += blockDim.x) {
+    const int s = idx / OT, oo = idx - s * OT;
+    const int oc = o0 + oo;
+    float v = 0.f;
+    if (oc < Cout) v = TRANSPOSE ? Wm[(size_t)s * Ci + oc] : Wm[(size_t)oc * Ci + s];
+    ws[idx] = v;
+  }
+  float* bs = ws + Cin * OT;
+  for (int idx = threadIdx.x; idx < OT; idx += blockDim.x)
+    bs[idx] = (bias != nullptr && o0 + idx < Cout) ? bias[o0 + idx] : 0.f;
+  __syncthreads();
+
+  const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= N2) return;
+  float2 acc[OT];
+#pragma unroll
+  for (int oo = 0; oo < OT; ++oo) acc[oo] = make_float2(bs[oo], bs[oo]);
+  const float2* __restrict__ ip = reinterpret_cast<const float2*>(in) + (size_t)b * Cin * N2 + p;
+  for (int s0 = 0; s0 < Cin; s0 += PW_CH) {
+    float2 xv[PW_CH];
+#pragma unroll
+    for (int u = 0; u < PW_CH; ++u)
+      xv[u] = (s0 + u < Cin) ? __ldg(ip + (size_t)(s0 + u) * N2) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < PW_CH; ++u) {
+      if (s0 + u < Cin) {
+        const float4* wrow = reinterpret_cast<const float4*>(ws + (s0 + u) * OT);
+#pragma unroll
+        for (int q = 0; q < OT / 4; ++q) {
+          const float4 w = wrow[q];
+          acc[4 * q + 0].x = fmaf(w.x, xv[u].x, acc[4 * q + 0].x); acc[4 * q + 0].y = fmaf(w.x, xv[u].y, acc[4 * q + 0].y);
+          acc[4 * q + 1].x = fmaf(w.y, xv[u].x, acc[4 * q + 1].x); acc[4 * q + 1].y = fmaf(w.y, xv[u].y, acc[4 * q + 1].y);
+          acc[4 * q + 2].x = fmaf(w.z, xv[u].x, acc[4 * q + 2].x); acc[4 * q + 2].y = fmaf(w.z, xv[u].y, acc[4 * q + 2].y);
+          acc[4 * q + 3].x = fmaf(w.w, xv[u].x, acc[4 * q + 3].x); acc[4 * q + 3].y = fmaf(w.w, xv[u].y, acc[4 * q + 3].y);
+        }
+      }
+    }
+  }
+  float2* __restrict__ op = reinterpret_cast<float2*>(out) + (size_t)b * Cout * N2 + p;
+#pragma unroll
+  for (int oo = 0; oo < OT; ++oo) {
+    if (o0 + oo >= Cout) break;
+    op[(size_t)(o0 + oo) * N2] = acc[oo];
+  }
+}
+
+template <int OT>
+int launch_pw2(const float* in, const float* Wm, const float* bias, float* out, int B, int Co, int Ci, long N,
+               int transpose, cudaStream_t st) {
+  const int Cin = transpose ? Co : Ci;
+  const int Cout = transpose ? Ci : Co;
+  const long N2 = N / 2;
+  dim3 grid((unsigned)((N2 + 255) / 256), (Cout + OT - 1) / OT, B);
+  const size_t smem = sizeof(float) * ((size_t)Cin * OT + OT);
+  if (transpose)
+    pointwise2_kernel<OT, true><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
+  else
+    pointwise2_kernel<OT, false><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
+  count_launch();
+  return check_launch("pointwise2_kernel");
+}
+
 template <int OT, int VEC>
 int launch_pw(const float* in, const float* Wm, const float* bias, float* out, int B, int Co, int Ci, long N,
               int transpose, cudaStream_t st) {
@@ -211,6 +287,163 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2 of the weight gradient: TMA-fed (cp.async.bulk, 1-D) slabs with an mbarrier full/empty ring.
+// A producer warp streams slab after slab -- one bulk copy of KT pixels per channel row of ds and
+// of a -- into a WG2_STAGES-deep ring; consumer warps each own one T x T output tile with lanes
+// over pixel quads (LDS.128: 2T loads per 4 T^2 FMA).  Nothing but the bulk copies touches global
+// memory in the steady state, so the kernel streams at the HBM rate set by its 8 bytes/pixel/channel.
+// ------------------------------------------------------------------------------------------
+constexpr int WG2_STAGES = 4;
+constexpr int WG2_MAXW = 8;      // consumer warps per CTA
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int T>
+__global__ void __launch_bounds__(32 * (WG2_MAXW + 1))
+wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co,
+                      int Ci, long N, int slabs_per_sample, long total_slabs, long slabs_per_cta, int tiles_i,
+                      int ntiles, int nwarps) {
+  extern __shared__ __align__(16) float sm[];   // WG2_STAGES x ([Co][KT] ds slab, [Ci][KT] a slab), then barriers
+  const int rows = Co + Ci;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)WG2_STAGES * rows * KT);
+  unsigned long long* empty = full + WG2_STAGES;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG2_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, nwarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  long s_begin = (long)blockIdx.x * slabs_per_cta;
+  long s_end = s_begin + slabs_per_cta;
+  if (s_end > total_slabs) s_end = total_slabs;
+
+  if (warp == nwarps) {
+    // ---- producer warp ---------------------------------------------------------------------
+    for (long slab = s_begin; slab < s_end; ++slab) {
+      const int it = (int)(slab - s_begin);
+      const int stage = it % WG2_STAGES;
+      const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
+      mbar_wait(empty + stage, ph ^ 1u);
+      const long b = slab / slabs_per_sample;
+      const long k0 = (slab - b * slabs_per_sample) * KT;
+      const long left = N - k0;
+      const unsigned bytes = (unsigned)((left < KT ? left : KT) * sizeof(float));
+      float* dst = sm + (size_t)stage * rows * KT;
+      if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes * (unsigned)rows);
+      __syncwarp();
+      for (int c = lane; c < rows; c += 32) {
+        const float* src = (c < Co) ? (ds + ((size_t)b * Co + c) * N + k0) : (a + ((size_t)b * Ci + (c - Co)) * N + k0);
+        bulk_g2s(dst + (size_t)c * KT, src, bytes, full + stage);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps: one T x T tile each -------------------------------------------------
+  const int tile = blockIdx.y * nwarps + warp;
+  const bool has_tile = tile < ntiles;
+  const int to = has_tile ? (tile / tiles_i) * T : 0;
+  const int ti = has_tile ? (tile % tiles_i) * T : 0;
+  const bool bias_tile = has_tile && (ti == 0);
+  float acc[T][T];
+  float accb[T];
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+    accb[r] = 0.f;
+#pragma unroll
+    for (int c = 0; c < T; ++c) acc[r][c] = 0.f;
+  }
+  for (long slab = s_begin; slab < s_end; ++slab) {
+    const int it = (int)(slab - s_begin);
+    const int stage = it % WG2_STAGES;
+    const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
+    mbar_wait(full + stage, ph);
+    const long b = slab / slabs_per_sample;
+    const long left = N - (slab - b * slabs_per_sample) * KT;
+    // pixel quad of this lane; a slab at the end of a sample is short by whole quads (N % 4 == 0)
+    if (has_tile && 4 * lane < left) {
+      const float* ds_s = sm + (size_t)stage * rows * KT + 4 * lane;
+      const float* a_s = ds_s + (size_t)Co * KT;
+      float4 dv[T];
+#pragma unroll
+      for (int r = 0; r < T; ++r)
+        dv[r] = (to + r < Co) ? *reinterpret_cast<const float4*>(ds_s + (to + r) * KT) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias_tile) {
+#pragma unroll
+        for (int r = 0; r < T; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
+      }
+#pragma unroll
+      for (int c = 0; c < T; ++c) {
+        const float4 av =
+            (ti + c < Ci) ? *reinterpret_cast<const float4*>(a_s + (ti + c) * KT) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < T; ++r) {
+          acc[r][c] = fmaf(dv[r].x, av.x, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].y, av.y, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].z, av.z, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].w, av.w, acc[r][c]);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + stage);
+  }
+  if (!has_tile) return;
+  float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
+#pragma unroll
+  for (int r = 0; r < T; ++r) {
+#pragma unroll
+    for (int c = 0; c < T; ++c) {
+      float v = acc[r][c];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && to + r < Co && ti + c < Ci) pp[(size_t)(to + r) * (Ci + 1) + ti + c] = v;
+    }
+    if (bias_tile) {
+      float v = accb[r];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && to + r < Co) pp[(size_t)(to + r) * (Ci + 1) + Ci] = v;
+    }
+  }
+}
+
 // one warp per output element: lanes stride the per-CTA partials, fixed-order shuffle tree
 __global__ void __launch_bounds__(128)
 wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gW, float* __restrict__ gb, int nparts,
@@ -248,6 +481,14 @@ extern "C" int fno_pointwise_fwd(const float* in, const float* W, const float* b
   if (B > 65535) { set_error("fno_pointwise_fwd: batch %d > 65535", B); return FNO_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Cout = transpose ? Ci : Co;
+  const int Cin = transpose ? Co : Ci;
+  const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) % 8 == 0);
+  if (vec2 && Cin <= 256) {
+    if (Cout % 20 == 0) return launch_pw2<20>(in, W, bias, out, B, Co, Ci, N, transpose, st);
+    if (Cout % 16 == 0) return launch_pw2<16>(in, W, bias, out, B, Co, Ci, N, transpose, st);
+    if (Cout % 8 == 0) return launch_pw2<8>(in, W, bias, out, B, Co, Ci, N, transpose, st);
+    return launch_pw2<4>(in, W, bias, out, B, Co, Ci, N, transpose, st);
+  }
   const bool vec4 = (N % 4 == 0) && ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) % 16 == 0);
   if (vec4) {
     if (Cout % 20 == 0) return launch_pw<20, 4>(in, W, bias, out, B, Co, Ci, N, transpose, st);
@@ -295,6 +536,25 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
   const int aligned = (N % 4 == 0) && ((reinterpret_cast<size_t>(ds) | reinterpret_cast<size_t>(a)) % 16 == 0);
   float* part = static_cast<float*>(work);
   dim3 grid((unsigned)ctas, ygroups);
+  const size_t smem2 = sizeof(float) * (size_t)WG2_STAGES * (Co + Ci) * KT + 2 * WG2_STAGES * sizeof(unsigned long long);
+  if (aligned && smem2 <= 200 * 1024) {
+    static std::atomic<int> attr2_done{0};
+    if (!attr2_done.load()) {
+      if (cudaFuncSetAttribute(wgrad2_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+          cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(wgrad2)");
+      attr2_done.store(1);
+    }
+    wgrad2_partial_kernel<T><<<grid, 32 * (warps + 1), smem2, st>>>(ds, a, part, Co, Ci, N, slabs_per_sample, total_slabs,
+                                                                    spc, tiles_i, ntiles, warps);
+    count_launch();
+    int rc2 = check_launch("wgrad2_partial_kernel");
+    if (rc2 != FNO_OK) return rc2;
+    const int total2 = Co * (Ci + 1);
+    wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas, Co, Ci);
+    count_launch();
+    return check_launch("wgrad_reduce_kernel");
+  }
   wgrad_partial_kernel<T><<<grid, 32 * warps, smem, st>>>(ds, a, part, Co, Ci, N, slabs_per_sample, total_slabs, spc,
                                                         tiles_i, ntiles, aligned);
   count_launch();

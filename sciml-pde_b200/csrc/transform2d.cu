@@ -3,24 +3,27 @@
 //
 // Both kernels share one factorisation (oracle/dft_oracle.py):
 //
-//   strided axis H ("column pass"):  one thread per (plane, w) column.  The 2*m1 kept signed
-//   frequencies {-m1..m1-1} are folded onto |k| = j in [0, m1]:  with
+//   strided axis H ("column pass"):  one thread per (plane, TN adjacent columns).  The 2*m1 kept
+//   signed frequencies {-m1..m1-1} are folded onto |k| = j in [0, m1]:  with
 //       A[j] = sum_h x[h] cos(2 pi j h / H),   B[j] = sum_h x[h] sin(2 pi j h / H)
 //   the column DFT is U[+j] = A[j] - i B[j], U[-j] = A[j] + i B[j]; rows are further folded in
 //   pairs (h, H-h): e = x[h] + x[H-h] feeds the cosines, o = x[h] - x[H-h] the sines.  That is
-//   2*m1+1 real accumulators per column and (2*m1+1) FMAs per row *pair*, the row twiddles being
-//   warp-uniform float4 broadcasts from shared memory.  x is read straight from global memory,
-//   exactly once, fully coalesced (lanes <-> consecutive w).
+//   2*m1+1 real accumulators per column and (2*m1+1) FMAs per row *pair*.  The row twiddles are
+//   warp-uniform float4 broadcasts from shared memory and are shared by the thread's TN columns,
+//   so a row pair costs (2*m1+1)/4 LDS.128 + 2 vector loads per TN*(2*m1+1) FFMA.  x is read
+//   straight from global memory, exactly once, coalesced (lanes <-> consecutive column groups).
 //
-//   contiguous axis W: the small [2*m1+1, W] x [W, m2] contraction runs from shared memory.
+//   contiguous axis W: the small [2*m1+1, W] x [W, 2*m2] contraction runs from shared memory as a
+//   register-tiled product (2 frequencies j x 4 wavenumbers k2 per thread, the W range split over
+//   several threads so that the whole CTA takes part), combined through shared memory.
 //
 // K3 mirrors it: the W-axis inverse is applied first to the tiny retained spectrum, leaving
 // 2*m1+1 real coefficients per column in registers; the H-axis pass then emits two output rows
 // (h, H-h) per (2*m1+1) FMAs and fuses "+ addend" (1x1-conv bypass), the optional store of the
 // pre-activation, and the exact-erf GELU.
 //
-// Several planes are flattened into one CTA (thread <-> (g, w), g < G) so that widths like
-// 130 = 4*32+2 do not waste a nearly empty warp per plane.
+// Several planes are flattened into one CTA (thread <-> (g, column group), g < G) so that widths
+// like 130 = 2 * 65 do not waste a nearly empty warp per plane.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -36,31 +39,75 @@ struct Geo {
   static constexpr int JP = (NJ + 3) & ~3;
 };
 
-// acc[0..M1T] += e * cos row, acc[M1T+1..2*M1T] += o * sin row  (row = JP floats, 16-B aligned)
-template <int M1T>
-__device__ __forceinline__ void fold_accumulate(float (&acc)[Geo<M1T>::NJ], const float* __restrict__ row,
-                                                float e, float o) {
-  constexpr int JP = Geo<M1T>::JP;
-  float tw[JP];
+template <int TN>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ static Vec ld(const float* p) { Vec r; r.v[0] = __ldg(p); return r; }
+  __device__ __forceinline__ static Vec ld_plain(const float* p) { Vec r; r.v[0] = *p; return r; }
+  __device__ __forceinline__ void st(float* p) const { *p = v[0]; }
+};
+template <>
+struct Vec<2> {
+  float v[2];
+  __device__ __forceinline__ static Vec ld(const float* p) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
+  }
+  __device__ __forceinline__ static Vec ld_plain(const float* p) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    Vec r; r.v[0] = t.x; r.v[1] = t.y; return r;
+  }
+  __device__ __forceinline__ void st(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+
+template <int JP>
+__device__ __forceinline__ void load_row(float (&tw)[JP], const float* __restrict__ row) {
   const float4* r4 = reinterpret_cast<const float4*>(row);
 #pragma unroll
   for (int q = 0; q < JP / 4; ++q) {
     const float4 v = r4[q];
-    tw[4 * q + 0] = v.x;
-    tw[4 * q + 1] = v.y;
-    tw[4 * q + 2] = v.z;
-    tw[4 * q + 3] = v.w;
+    tw[4 * q + 0] = v.x; tw[4 * q + 1] = v.y; tw[4 * q + 2] = v.z; tw[4 * q + 3] = v.w;
   }
-#pragma unroll
-  for (int j = 0; j <= M1T; ++j) acc[j] = fmaf(e, tw[j], acc[j]);
-#pragma unroll
-  for (int j = 1; j <= M1T; ++j) acc[M1T + j] = fmaf(o, tw[M1T + j], acc[M1T + j]);
 }
+
+// acc[n][0..M1T] += e[n] * cos row, acc[n][M1T+1..2*M1T] += o[n] * sin row
+template <int M1T, int TN>
+__device__ __forceinline__ void fold_accumulate(float (&acc)[TN][Geo<M1T>::NJ], const float* __restrict__ row,
+                                                const Vec<TN>& e, const Vec<TN>& o) {
+  float tw[Geo<M1T>::JP];
+  load_row<Geo<M1T>::JP>(tw, row);
+#pragma unroll
+  for (int j = 0; j <= M1T; ++j)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[n][j] = fmaf(e.v[n], tw[j], acc[n][j]);
+#pragma unroll
+  for (int j = 1; j <= M1T; ++j)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[n][M1T + j] = fmaf(o.v[n], tw[M1T + j], acc[n][M1T + j]);
+}
+
+// cosine part only (self-paired rows h = 0 and h = H/2 have no odd component)
+template <int M1T, int TN>
+__device__ __forceinline__ void fold_accumulate_even(float (&acc)[TN][Geo<M1T>::NJ], const float* __restrict__ row,
+                                                     const Vec<TN>& e) {
+  float tw[Geo<M1T>::JP];
+  load_row<Geo<M1T>::JP>(tw, row);
+#pragma unroll
+  for (int j = 0; j <= M1T; ++j)
+#pragma unroll
+    for (int n = 0; n < TN; ++n) acc[n][j] = fmaf(e.v[n], tw[j], acc[n][j]);
+}
+
+constexpr int S2_JT = 2;   // stage-2 tile: frequencies j per thread
+constexpr int S2_KT = 4;   //               wavenumbers k2 per thread
+constexpr int S2_ACC = S2_JT * S2_KT * 4;
 
 // ------------------------------------------------------------------------------------------
 // K1
 // ------------------------------------------------------------------------------------------
-template <int M1T, bool PREMUL, int MAXT, int MINB>
+template <int M1T, int TN, bool PREMUL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, float* __restrict__ ds_out,
              float2* __restrict__ X, const float* __restrict__ twH, const float* __restrict__ twW,
@@ -71,12 +118,18 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
   extern __shared__ __align__(16) float smem[];
   float* twH_s = smem;                       // [NP][JP]
   float* twW_s = twH_s + NP * JP;            // [2][m2][WP]
-  float* uab = twW_s + 2 * m2 * WP;          // [G][NJ][WP]
+  float* uab = twW_s + 2 * m2 * WP;          // [G][NJ][WP]   (re-used for the stage-2 partial sums)
 
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
-  for (int i = tid; i < NP * JP; i += nthr) twH_s[i] = twH[i];
-  for (int i = tid; i < 2 * m2 * WP; i += nthr) twW_s[i] = twW[i];
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(twH);
+    float4* d4 = reinterpret_cast<float4*>(twH_s);
+    for (int i = tid; i < NP * JP / 4; i += nthr) d4[i] = __ldg(s4 + i);
+    s4 = reinterpret_cast<const float4*>(twW);
+    d4 = reinterpret_cast<float4*>(twW_s);
+    for (int i = tid; i < 2 * m2 * WP / 4; i += nthr) d4[i] = __ldg(s4 + i);
+  }
   // zero the pad columns of uab (read by the float4 loops of stage 2)
   const int padw = WP - W;
   if (padw > 0) {
@@ -87,116 +140,200 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
   }
   __syncthreads();
 
-  // ---- column pass over H ------------------------------------------------------------------
-  const int g = tid / W;
-  const int w = tid - g * W;
+  // ---- stage 1: column pass over H ----------------------------------------------------------
+  const int tpp = W / TN;                    // threads per plane
+  const int g = tid / tpp;
+  const int w0 = (tid - g * tpp) * TN;
   const long plane = (long)blockIdx.x * G + g;
-  const bool active = (g < G) && (plane < planes);
-  if (active) {
-    float acc[NJ];
+  if (g < G) {
+    float acc[TN][NJ];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.0f;
-    const size_t base = (size_t)plane * H * W + w;
-    const float* __restrict__ xp = x + base;
-    auto load = [&](int h) -> float {
-      float v = __ldg(xp + (size_t)h * W);
-      if (PREMUL) {
-        v *= gelu_exact_grad(__ldg(preact + base + (size_t)h * W));
-        if (ds_out != nullptr) ds_out[base + (size_t)h * W] = v;
+    for (int n = 0; n < TN; ++n)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) acc[n][j] = 0.0f;
+    if (plane < planes) {
+      const size_t base = (size_t)plane * H * W + w0;
+      const float* __restrict__ xp = x + base;
+      const float* __restrict__ sp = PREMUL ? preact + base : nullptr;
+      float* __restrict__ dp = (PREMUL && ds_out != nullptr) ? ds_out + base : nullptr;
+      auto finish = [&](Vec<TN> v, const Vec<TN>& s, int h) -> Vec<TN> {
+        if (PREMUL) {
+#pragma unroll
+          for (int n = 0; n < TN; ++n) v.v[n] *= gelu_fast_grad(s.v[n]);
+          if (dp != nullptr) v.st(dp + h * W);
+        }
+        return v;
+      };
+      auto load1 = [&](int h) -> Vec<TN> {
+        const Vec<TN> v = Vec<TN>::ld(xp + h * W);
+        Vec<TN> s = v;
+        if (PREMUL) s = Vec<TN>::ld(sp + h * W);
+        return finish(v, s, h);
+      };
+      fold_accumulate_even<M1T, TN>(acc, twH_s, load1(0));
+      const int npairs = (H - 1) / 2;
+      // PG row pairs per step: all loads of a step are issued before the FMAs that consume them
+      // (memory-level parallelism per thread; the resident warps provide the rest)
+      constexpr int PG = PREMUL ? 2 : 4;
+      int t = 1;
+      for (; t + PG - 1 <= npairs; t += PG) {
+        Vec<TN> v1[PG], v2[PG], s1[PG], s2[PG];
+#pragma unroll
+        for (int u = 0; u < PG; ++u) {
+          v1[u] = Vec<TN>::ld(xp + (t + u) * W);
+          v2[u] = Vec<TN>::ld(xp + (H - t - u) * W);
+          if (PREMUL) {
+            s1[u] = Vec<TN>::ld(sp + (t + u) * W);
+            s2[u] = Vec<TN>::ld(sp + (H - t - u) * W);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PG; ++u) {
+          const Vec<TN> a = finish(v1[u], s1[u], t + u), b = finish(v2[u], s2[u], H - t - u);
+          Vec<TN> e, o;
+#pragma unroll
+          for (int n = 0; n < TN; ++n) { e.v[n] = a.v[n] + b.v[n]; o.v[n] = a.v[n] - b.v[n]; }
+          fold_accumulate<M1T, TN>(acc, twH_s + (t + u) * JP, e, o);
+        }
       }
-      return v;
-    };
-    // h = 0 (self-paired)
-    fold_accumulate<M1T>(acc, twH_s, load(0), 0.0f);
-    const int npairs = (H - 1) / 2;
-    // PG row pairs per step: all 2*PG global loads are issued before the FMAs that consume them,
-    // which is what keeps enough bytes in flight per SM (the kernel has no other latency hiding
-    // than its own memory-level parallelism and the other resident warps)
-    constexpr int PG = 4;
-    int t = 1;
-    for (; t + PG - 1 <= npairs; t += PG) {
-      float v1[PG], v2[PG];
+      for (; t <= npairs; ++t) {
+        const Vec<TN> a = load1(t), b = load1(H - t);
+        Vec<TN> e, o;
 #pragma unroll
-      for (int u = 0; u < PG; ++u) {
-        v1[u] = load(t + u);
-        v2[u] = load(H - t - u);
+        for (int n = 0; n < TN; ++n) { e.v[n] = a.v[n] + b.v[n]; o.v[n] = a.v[n] - b.v[n]; }
+        fold_accumulate<M1T, TN>(acc, twH_s + t * JP, e, o);
       }
-#pragma unroll
-      for (int u = 0; u < PG; ++u) fold_accumulate<M1T>(acc, twH_s + (t + u) * JP, v1[u] + v2[u], v1[u] - v2[u]);
+      if ((H & 1) == 0) fold_accumulate_even<M1T, TN>(acc, twH_s + (H / 2) * JP, load1(H / 2));
     }
-    for (; t <= npairs; ++t) {
-      const float v1 = load(t);
-      const float v2 = load(H - t);
-      fold_accumulate<M1T>(acc, twH_s + t * JP, v1 + v2, v1 - v2);
+    float* urow = uab + (size_t)g * NJ * WP + w0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      Vec<TN> v;
+#pragma unroll
+      for (int n = 0; n < TN; ++n) v.v[n] = acc[n][j];
+      v.st(urow + j * WP);
     }
-    if ((H & 1) == 0) fold_accumulate<M1T>(acc, twH_s + (H / 2) * JP, load(H / 2), 0.0f);
-    float* urow = uab + (size_t)g * NJ * WP + w;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) urow[j * WP] = acc[j];
-  } else if (g < G) {
-    float* urow = uab + (size_t)g * NJ * WP + w;
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) urow[j * WP] = 0.0f;
   }
   __syncthreads();
 
-  // ---- contraction over W from shared memory -------------------------------------------------
-  // item = (g, j, pair of k2): four real sums per k2
+  // ---- stage 2: contraction over W from shared memory --------------------------------------
+  // tile = (plane gg, S2_JT frequencies j, S2_KT wavenumbers k2, slice ks of the W range); per (j, k2):
   //   P1 = sum A cos, P2 = sum A sin, P3 = sum B cos, P4 = sum B sin
   //   X[+j, k2] = (P1 - P4) - i (P2 + P3),   X[-j, k2] = (P1 + P4) + i (P3 - P2)
-  const int K2P = (m2 + 1) >> 1;
-  const int nitems = G * (m1 + 1) * K2P;
+  const int nJG = (m1 + S2_JT) / S2_JT;            // ceil((m1 + 1) / JT)
+  const int nKG = (m2 + S2_KT - 1) / S2_KT;
+  const int ntiles = G * nJG * nKG;
   const int W4 = WP >> 2;
+  int KS = nthr / ntiles;                          // W-range slices per tile (0 if ntiles > nthr)
+  if (KS > W4) KS = W4;
+  // sliced partial sums are staged in the uab region once it is dead: bound KS by its capacity
+  while (KS > 1 && (size_t)ntiles * KS * S2_ACC > (size_t)G * NJ * WP) --KS;
   const bool nyq_even = ((W & 1) == 0);
-  for (int item = tid; item < nitems; item += nthr) {
-    const int kp = item % K2P;
-    const int j = (item / K2P) % (m1 + 1);
-    const int gg = item / (K2P * (m1 + 1));
-    const long pl = (long)blockIdx.x * G + gg;
-    if (pl >= planes) continue;
-    const int k2a = 2 * kp;
-    const int k2b = (k2a + 1 < m2) ? k2a + 1 : k2a;  // clamp: duplicate work, not stored
-    const float4* A4 = reinterpret_cast<const float4*>(uab + ((size_t)gg * NJ + j) * WP);
-    const float4* B4 = reinterpret_cast<const float4*>(uab + ((size_t)gg * NJ + M1T + (j > 0 ? j : 1)) * WP);
-    const float bmask = (j > 0) ? 1.0f : 0.0f;
-    const float4* Ca = reinterpret_cast<const float4*>(twW_s + (size_t)k2a * WP);
-    const float4* Sa = reinterpret_cast<const float4*>(twW_s + (size_t)(m2 + k2a) * WP);
-    const float4* Cb = reinterpret_cast<const float4*>(twW_s + (size_t)k2b * WP);
-    const float4* Sb = reinterpret_cast<const float4*>(twW_s + (size_t)(m2 + k2b) * WP);
-    float p1a = 0.f, p2a = 0.f, p3a = 0.f, p4a = 0.f, p1b = 0.f, p2b = 0.f, p3b = 0.f, p4b = 0.f;
-#pragma unroll 2
-    for (int q = 0; q < W4; ++q) {
-      const float4 a = A4[q];
-      const float4 b = B4[q];
-      const float4 ca = Ca[q], sa = Sa[q], cb = Cb[q], sb = Sb[q];
-#define FNO_DOT4(P, U, V)      \
-  P = fmaf(U.x, V.x, P);       \
-  P = fmaf(U.y, V.y, P);       \
-  P = fmaf(U.z, V.z, P);       \
-  P = fmaf(U.w, V.w, P);
-      FNO_DOT4(p1a, a, ca) FNO_DOT4(p2a, a, sa) FNO_DOT4(p3a, b, ca) FNO_DOT4(p4a, b, sa)
-      FNO_DOT4(p1b, a, cb) FNO_DOT4(p2b, a, sb) FNO_DOT4(p3b, b, cb) FNO_DOT4(p4b, b, sb)
-#undef FNO_DOT4
-    }
-    p3a *= bmask; p4a *= bmask; p3b *= bmask; p4b *= bmask;
-    float2* Xp = X + (size_t)pl * (2 * m1) * m2;
+
+  // partial sums of one tile over the float4 chunks [q0, q1) of the W range
+  auto tile_sums = [&](float (&pacc)[S2_ACC], int tile, int q0, int q1) {
+    const int kg = tile % nKG;
+    const int jg = (tile / nKG) % nJG;
+    const int gg = tile / (nKG * nJG);
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int k2 = s ? k2a + 1 : k2a;
-      if (k2 >= m2) break;
-      const float p1 = s ? p1b : p1a, p2 = s ? p2b : p2a, p3 = s ? p3b : p3a, p4 = s ? p4b : p4a;
-      float sc = scale;
-      if (cmode && k2 != 0 && !(nyq_even && 2 * k2 == W)) sc *= 2.0f;
-      if (j < m1) Xp[(size_t)j * m2 + k2] = make_float2((p1 - p4) * sc, -(p2 + p3) * sc);
-      if (j >= 1) Xp[(size_t)(2 * m1 - j) * m2 + k2] = make_float2((p1 + p4) * sc, (p3 - p2) * sc);
+    for (int i = 0; i < S2_ACC; ++i) pacc[i] = 0.f;
+    const float4* A4[S2_JT];
+    const float4* B4[S2_JT];
+#pragma unroll
+    for (int a = 0; a < S2_JT; ++a) {
+      int j = jg * S2_JT + a;
+      if (j > m1) j = m1;                           // clamp: duplicate work, not stored
+      A4[a] = reinterpret_cast<const float4*>(uab + ((size_t)gg * NJ + j) * WP);
+      B4[a] = reinterpret_cast<const float4*>(uab + ((size_t)gg * NJ + M1T + (j > 0 ? j : 1)) * WP);
     }
+    const float4* C4[S2_KT];
+    const float4* S4[S2_KT];
+#pragma unroll
+    for (int b = 0; b < S2_KT; ++b) {
+      int k2 = kg * S2_KT + b;
+      if (k2 >= m2) k2 = m2 - 1;
+      C4[b] = reinterpret_cast<const float4*>(twW_s + (size_t)k2 * WP);
+      S4[b] = reinterpret_cast<const float4*>(twW_s + (size_t)(m2 + k2) * WP);
+    }
+    for (int q = q0; q < q1; ++q) {
+      float4 av[S2_JT], bv[S2_JT];
+#pragma unroll
+      for (int a = 0; a < S2_JT; ++a) { av[a] = A4[a][q]; bv[a] = B4[a][q]; }
+#pragma unroll
+      for (int b = 0; b < S2_KT; ++b) {
+        const float4 c = C4[b][q], sn = S4[b][q];
+#pragma unroll
+        for (int a = 0; a < S2_JT; ++a) {
+          float* p = pacc + (a * S2_KT + b) * 4;
+#define FNO_DOT4(P, U, V) P = fmaf(U.x, V.x, P); P = fmaf(U.y, V.y, P); P = fmaf(U.z, V.z, P); P = fmaf(U.w, V.w, P);
+          FNO_DOT4(p[0], av[a], c) FNO_DOT4(p[1], av[a], sn) FNO_DOT4(p[2], bv[a], c) FNO_DOT4(p[3], bv[a], sn)
+#undef FNO_DOT4
+        }
+      }
+    }
+  };
+  // stores the two signed-frequency outputs of (tile, pair pi) from p = (P1, P2, P3, P4)
+  auto emit_pair = [&](int tile, int pi, float4 p) {
+    const int kg = tile % nKG;
+    const int jg = (tile / nKG) % nJG;
+    const int gg = tile / (nKG * nJG);
+    const int a = pi / S2_KT, b = pi - a * S2_KT;
+    const int j = jg * S2_JT + a, k2 = kg * S2_KT + b;
+    const long pl = (long)blockIdx.x * G + gg;
+    if (j > m1 || k2 >= m2 || pl >= planes) return;
+    if (j == 0) { p.z = 0.f; p.w = 0.f; }
+    float sc = scale;
+    if (cmode && k2 != 0 && !(nyq_even && 2 * k2 == W)) sc *= 2.0f;
+    float2* Xp = X + (size_t)pl * (2 * m1) * m2;
+    if (j < m1) Xp[(size_t)j * m2 + k2] = make_float2((p.x - p.w) * sc, -(p.y + p.z) * sc);
+    if (j >= 1) Xp[(size_t)(2 * m1 - j) * m2 + k2] = make_float2((p.x + p.w) * sc, (p.z - p.y) * sc);
+  };
+
+  float pacc[S2_ACC];
+  if (KS <= 1) {
+    // more tiles than spare threads: each thread owns whole tiles
+    for (int tile = tid; tile < ntiles; tile += nthr) {
+      tile_sums(pacc, tile, 0, W4);
+#pragma unroll
+      for (int pi = 0; pi < S2_JT * S2_KT; ++pi)
+        emit_pair(tile, pi, make_float4(pacc[4 * pi], pacc[4 * pi + 1], pacc[4 * pi + 2], pacc[4 * pi + 3]));
+    }
+    return;
+  }
+  // KS threads per tile, each over a slice of the W range; partial sums combined through shared
+  // memory (the uab region, dead after the barrier)
+  const bool live = tid < ntiles * KS;
+  const int ks = live ? tid / ntiles : 0;
+  const int tile = live ? tid - ks * ntiles : 0;
+  const int cps = (W4 + KS - 1) / KS;
+  if (live) {
+    const int q0 = ks * cps;
+    tile_sums(pacc, tile, q0, (q0 + cps < W4) ? q0 + cps : W4);
+  }
+  __syncthreads();
+  float* red = uab;                                 // [KS][ntiles][S2_ACC]
+  if (live) {
+    float4* r4 = reinterpret_cast<float4*>(red + (size_t)tid * S2_ACC);
+#pragma unroll
+    for (int i = 0; i < S2_ACC / 4; ++i)
+      r4[i] = make_float4(pacc[4 * i], pacc[4 * i + 1], pacc[4 * i + 2], pacc[4 * i + 3]);
+  }
+  __syncthreads();
+  if (!live) return;
+  for (int pi = ks; pi < S2_JT * S2_KT; pi += KS) {
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sl = 0; sl < KS; ++sl) {
+      const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)(sl * ntiles + tile) * S2_ACC) + pi * 4);
+      p.x += v.x; p.y += v.y; p.z += v.z; p.w += v.w;
+    }
+    emit_pair(tile, pi, p);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------
-template <int M1T, int MAXT, int MINB>
+template <int M1T, int TN, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restrict__ s_out, float* out,
              const float* __restrict__ twH, const float* __restrict__ twW, int H, int W, int WP, int m1,
@@ -211,8 +348,14 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
 
   const int tid = threadIdx.x;
   const int nthr = blockDim.x;
-  for (int i = tid; i < NP * JP; i += nthr) twH_s[i] = twH[i];
-  for (int i = tid; i < 2 * m2 * WP; i += nthr) twW_s[i] = twW[i];
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(twH);
+    float4* d4 = reinterpret_cast<float4*>(twH_s);
+    for (int i = tid; i < NP * JP / 4; i += nthr) d4[i] = __ldg(s4 + i);
+    s4 = reinterpret_cast<const float4*>(twW);
+    d4 = reinterpret_cast<float4*>(twW_s);
+    for (int i = tid; i < 2 * m2 * WP / 4; i += nthr) d4[i] = __ldg(s4 + i);
+  }
   // stage 0: fold the +j / -j spectrum rows:  Yp = Y[+j] + Y[-j],  Dm = Y[-j] - Y[+j], pre-scaled
   const bool nyq_even = ((W & 1) == 0);
   for (int i = tid; i < G * m2 * NC; i += nthr) {
@@ -224,8 +367,8 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
     if (pl < planes && j <= m1) {
       const float2* Yp = Y + (size_t)pl * (2 * m1) * m2;
       float2 yp_ = make_float2(0.f, 0.f), ym_ = make_float2(0.f, 0.f);
-      if (j < m1) yp_ = Yp[(size_t)j * m2 + k2];
-      if (j >= 1) ym_ = Yp[(size_t)(2 * m1 - j) * m2 + k2];
+      if (j < m1) yp_ = __ldg(Yp + (size_t)j * m2 + k2);
+      if (j >= 1) ym_ = __ldg(Yp + (size_t)(2 * m1 - j) * m2 + k2);
       float sc = scale;
       if (cmode && k2 != 0 && !(nyq_even && 2 * k2 == W)) sc *= 2.0f;
       v = make_float4((yp_.x + ym_.x) * sc, (yp_.y + ym_.y) * sc, (ym_.x - yp_.x) * sc, (ym_.y - yp_.y) * sc);
@@ -234,109 +377,138 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
   }
   __syncthreads();
 
-  const int g = tid / W;
-  const int w = tid - g * W;
+  const int tpp = W / TN;
+  const int g = tid / tpp;
+  const int w0 = (tid - g * tpp) * TN;
   const long plane = (long)blockIdx.x * G + g;
   if (!((g < G) && (plane < planes))) return;
 
   // stage A: W-axis inverse on the retained spectrum -> per-column coefficients in registers
   //   out[h, w] = sum_j Cc[j] cos(2 pi j h / H) + Ss[j] sin(2 pi j h / H)
-  float cc[NC], ss[NC];
+  float cc[TN][NC], ss[TN][NC];
 #pragma unroll
-  for (int j = 0; j < NC; ++j) { cc[j] = 0.f; ss[j] = 0.f; }
+  for (int n = 0; n < TN; ++n)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) { cc[n][j] = 0.f; ss[n][j] = 0.f; }
   for (int k2 = 0; k2 < m2; ++k2) {
-    const float c = twW_s[(size_t)k2 * WP + w];
-    const float s = twW_s[(size_t)(m2 + k2) * WP + w];
+    const Vec<TN> c = Vec<TN>::ld_plain(twW_s + (size_t)k2 * WP + w0);
+    const Vec<TN> s = Vec<TN>::ld_plain(twW_s + (size_t)(m2 + k2) * WP + w0);
     const float4* q4 = yp + ((size_t)g * m2 + k2) * NC;
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
       const float4 q = q4[j];
-      cc[j] = fmaf(q.x, c, cc[j]);
-      cc[j] = fmaf(-q.y, s, cc[j]);
-      if (j > 0) {
-        ss[j] = fmaf(q.z, s, ss[j]);
-        ss[j] = fmaf(q.w, c, ss[j]);
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        cc[n][j] = fmaf(q.x, c.v[n], cc[n][j]);
+        cc[n][j] = fmaf(-q.y, s.v[n], cc[n][j]);
+        if (j > 0) {
+          ss[n][j] = fmaf(q.z, s.v[n], ss[n][j]);
+          ss[n][j] = fmaf(q.w, c.v[n], ss[n][j]);
+        }
       }
     }
   }
 
   // stage B: H-axis pass, two rows per step, fused epilogue
-  const size_t base = (size_t)plane * H * W + w;
+  const size_t base = (size_t)plane * H * W + w0;
   const bool has_add = addend != nullptr;
-  auto ld_add = [&](int h) -> float { return has_add ? addend[base + (size_t)h * W] : 0.f; };
-  auto emit = [&](int h, float v) {
-    const size_t idx = base + (size_t)h * W;
-    if (s_out != nullptr) s_out[idx] = v;
-    if (apply_gelu) v = gelu_exact(v);
-    out[idx] = v;
+  const float* ap = has_add ? addend + base : nullptr;
+  float* __restrict__ sop = s_out != nullptr ? s_out + base : nullptr;
+  float* op = out + base;
+  auto ld_add = [&](int h) -> Vec<TN> {
+    if (has_add) return Vec<TN>::ld_plain(ap + h * W);
+    Vec<TN> z;
+#pragma unroll
+    for (int n = 0; n < TN; ++n) z.v[n] = 0.f;
+    return z;
   };
-  auto eval = [&](int t, float& e, float& o) {
-    const float4* r4 = reinterpret_cast<const float4*>(twH_s + (size_t)t * JP);
+  auto emit = [&](int h, Vec<TN> v) {
+    if (sop != nullptr) v.st(sop + h * W);
+    if (apply_gelu) {
+#pragma unroll
+      for (int n = 0; n < TN; ++n) v.v[n] = gelu_fast(v.v[n]);
+    }
+    v.st(op + h * W);
+  };
+  auto eval = [&](int t, Vec<TN>& e, Vec<TN>& o) {
     float tw[JP];
+    load_row<JP>(tw, twH_s + (size_t)t * JP);
 #pragma unroll
-    for (int q = 0; q < JP / 4; ++q) {
-      const float4 v = r4[q];
-      tw[4 * q + 0] = v.x; tw[4 * q + 1] = v.y; tw[4 * q + 2] = v.z; tw[4 * q + 3] = v.w;
-    }
-    float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;
+    for (int n = 0; n < TN; ++n) {
+      float e0 = 0.f, e1 = 0.f, o0 = 0.f, o1 = 0.f;
 #pragma unroll
-    for (int j = 0; j <= M1T; ++j) {
-      if (j & 1) e1 = fmaf(cc[j], tw[j], e1); else e0 = fmaf(cc[j], tw[j], e0);
-    }
+      for (int j = 0; j <= M1T; ++j) {
+        if (j & 1) e1 = fmaf(cc[n][j], tw[j], e1); else e0 = fmaf(cc[n][j], tw[j], e0);
+      }
 #pragma unroll
-    for (int j = 1; j <= M1T; ++j) {
-      if (j & 1) o1 = fmaf(ss[j], tw[M1T + j], o1); else o0 = fmaf(ss[j], tw[M1T + j], o0);
+      for (int j = 1; j <= M1T; ++j) {
+        if (j & 1) o1 = fmaf(ss[n][j], tw[M1T + j], o1); else o0 = fmaf(ss[n][j], tw[M1T + j], o0);
+      }
+      e.v[n] = e0 + e1;
+      o.v[n] = o0 + o1;
     }
-    e = e0 + e1;
-    o = o0 + o1;
   };
   {
-    float e, o;
-    const float a0 = ld_add(0);
+    Vec<TN> e, o;
+    const Vec<TN> a0 = ld_add(0);
     eval(0, e, o);
-    emit(0, e + a0);
+#pragma unroll
+    for (int n = 0; n < TN; ++n) e.v[n] += a0.v[n];
+    emit(0, e);
   }
   const int npairs = (H - 1) / 2;
   // `addend` may alias `out` (in-place epilogue), so the compiler cannot move a load above an
   // earlier store; the loads of a whole group of PG row pairs are therefore issued by hand before
   // any of the group's stores, and the next group's loads before this group's arithmetic.
-  constexpr int PG = 4;
+  constexpr int PG = (TN == 2) ? 2 : 4;
   int t = 1;
-  float a1[PG], a2[PG];
+  Vec<TN> a1[PG], a2[PG];
   if (t + PG - 1 <= npairs) {
 #pragma unroll
     for (int u = 0; u < PG; ++u) { a1[u] = ld_add(t + u); a2[u] = ld_add(H - t - u); }
   }
   for (; t + PG - 1 <= npairs; t += PG) {
-    float n1[PG], n2[PG];
+    Vec<TN> n1[PG], n2[PG];
     const bool more = (t + 2 * PG - 1 <= npairs);
 #pragma unroll
     for (int u = 0; u < PG; ++u) {
-      n1[u] = more ? ld_add(t + PG + u) : 0.f;
-      n2[u] = more ? ld_add(H - t - PG - u) : 0.f;
+      if (more) { n1[u] = ld_add(t + PG + u); n2[u] = ld_add(H - t - PG - u); }
+      else { n1[u] = a1[u]; n2[u] = a2[u]; }
     }
 #pragma unroll
     for (int u = 0; u < PG; ++u) {
-      float e, o;
+      Vec<TN> e, o, up, dn;
       eval(t + u, e, o);
-      emit(t + u, e + o + a1[u]);
-      emit(H - t - u, e - o + a2[u]);
+#pragma unroll
+      for (int n = 0; n < TN; ++n) {
+        up.v[n] = e.v[n] + o.v[n] + a1[u].v[n];
+        dn.v[n] = e.v[n] - o.v[n] + a2[u].v[n];
+      }
+      emit(t + u, up);
+      emit(H - t - u, dn);
     }
 #pragma unroll
     for (int u = 0; u < PG; ++u) { a1[u] = n1[u]; a2[u] = n2[u]; }
   }
   for (; t <= npairs; ++t) {
-    float e, o;
-    const float b1 = ld_add(t), b2 = ld_add(H - t);
+    Vec<TN> e, o, up, dn;
+    const Vec<TN> b1 = ld_add(t), b2 = ld_add(H - t);
     eval(t, e, o);
-    emit(t, e + o + b1);
-    emit(H - t, e - o + b2);
+#pragma unroll
+    for (int n = 0; n < TN; ++n) {
+      up.v[n] = e.v[n] + o.v[n] + b1.v[n];
+      dn.v[n] = e.v[n] - o.v[n] + b2.v[n];
+    }
+    emit(t, up);
+    emit(H - t, dn);
   }
   if ((H & 1) == 0) {
-    float e, o;
-    const float b1 = ld_add(H / 2);
+    Vec<TN> e, o;
+    const Vec<TN> b1 = ld_add(H / 2);
     eval(H / 2, e, o);
-    emit(H / 2, e + b1);
+#pragma unroll
+    for (int n = 0; n < TN; ++n) e.v[n] += b1.v[n];
+    emit(H / 2, e);
   }
 }
 
@@ -352,11 +524,14 @@ size_t inv_smem_bytes(const Plan* p, int G) {
          sizeof(float4) * (size_t)G * p->m2 * (p->M1T + 1);
 }
 
-template <int M1T, int MAXT, int MINB>
+// columns per thread: two when the width is even and the accumulators still fit the register file
+inline int pick_tn(const Plan* p) { return ((p->W & 1) == 0 && p->M1T <= 16) ? 2 : 1; }
+
+template <int M1T, int TN, int MAXT, int MINB>
 int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
                  int cmode, float scale, cudaStream_t st, int threads, size_t smem, bool attr_only) {
-  auto k0 = fwd2d_kernel<M1T, false, MAXT, MINB>;
-  auto k1 = fwd2d_kernel<M1T, true, MAXT, MINB>;
+  auto k0 = fwd2d_kernel<M1T, TN, false, MAXT, MINB>;
+  auto k1 = fwd2d_kernel<M1T, TN, true, MAXT, MINB>;
   if (attr_only) {
     if (cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -375,11 +550,11 @@ int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_o
   return check_launch("fwd2d_kernel");
 }
 
-template <int M1T, int MAXT, int MINB>
+template <int M1T, int TN, int MAXT, int MINB>
 int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                  int cmode, float scale, int apply_gelu, cudaStream_t st, int threads, size_t smem,
                  bool attr_only) {
-  auto k = inv2d_kernel<M1T, MAXT, MINB>;
+  auto k = inv2d_kernel<M1T, TN, MAXT, MINB>;
   if (attr_only) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(inv2d)");
@@ -396,30 +571,52 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
 inline int round_threads(int n) { return (n + 31) & ~31; }
 constexpr size_t kMaxOptinSmem = 227 * 1024;  // sm_100: 232448 B opt-in per CTA
 
-template <int M1T>
-int dispatch_fwd(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
-                 int cmode, float scale, cudaStream_t st, bool attr_only) {
-  const int threads = round_threads(p->G_fwd * p->W);
+// launch-bound classes: <= 288 threads with 2 resident CTAs (<= 112 registers), <= 448 threads
+// alone on the SM (<= 144 registers), wider CTAs (very wide planes) at 64 registers
+template <int M1T, int TN>
+int dispatch_fwd_tn(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
+                    int cmode, float scale, cudaStream_t st, bool attr_only) {
+  const int threads = round_threads(p->G_fwd * (p->W / TN));
   // attr_only: opt every instantiation this plan can reach into the device maximum once; the
   // limit is per kernel function, so it must never be lowered by a later, smaller plan
   const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, p->G_fwd);
   if (threads <= 288)
-    return launch_fwd_t<M1T, 288, 3>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
-  if (threads <= 576)
-    return launch_fwd_t<M1T, 576, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
-  return launch_fwd_t<M1T, 1024, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+    return launch_fwd_t<M1T, TN, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+  if (threads <= 448)
+    return launch_fwd_t<M1T, TN, 448, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+  return launch_fwd_t<M1T, TN, 1024, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+}
+
+template <int M1T, int TN>
+int dispatch_inv_tn(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
+                    int cmode, float scale, int apply_gelu, cudaStream_t st, bool attr_only) {
+  const int threads = round_threads(p->G_inv * (p->W / TN));
+  const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, p->G_inv);
+  if (threads <= 288)
+    return launch_inv_t<M1T, TN, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+  if (threads <= 448)
+    return launch_inv_t<M1T, TN, 448, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+  return launch_inv_t<M1T, TN, 1024, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+}
+
+template <int M1T>
+int dispatch_fwd(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
+                 int cmode, float scale, cudaStream_t st, bool attr_only) {
+  if constexpr (M1T <= 16) {
+    if (pick_tn(p) == 2)
+      return dispatch_fwd_tn<M1T, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, attr_only);
+  }
+  return dispatch_fwd_tn<M1T, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, attr_only);
 }
 
 template <int M1T>
 int dispatch_inv(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                  int cmode, float scale, int apply_gelu, cudaStream_t st, bool attr_only) {
-  const int threads = round_threads(p->G_inv * p->W);
-  const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, p->G_inv);
-  if (threads <= 288)
-    return launch_inv_t<M1T, 288, 3>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
-  if (threads <= 576)
-    return launch_inv_t<M1T, 576, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
-  return launch_inv_t<M1T, 1024, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+  if constexpr (M1T <= 16) {
+    if (pick_tn(p) == 2)
+      return dispatch_inv_tn<M1T, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, attr_only);
+  }
+  return dispatch_inv_tn<M1T, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, attr_only);
 }
 
 }  // namespace
@@ -435,13 +632,20 @@ int dispatch_inv(const Plan* p, const float* Y, const float* addend, float* s_ou
     default: set_error("unsupported padded modes1 %d", p->M1T); return FNO_E_ARG; \
   }
 
+static bool misaligned8(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
+  return ((reinterpret_cast<size_t>(a) | reinterpret_cast<size_t>(b) | reinterpret_cast<size_t>(c) |
+           reinterpret_cast<size_t>(d)) & 7) != 0;
+}
+
 int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
                  int cmode, float scale, cudaStream_t st) {
+  if (misaligned8(x, preact, ds_out, X)) { set_error("fwd_transform: tensors must be 8-byte aligned"); return FNO_E_ARG; }
   FNO_DISPATCH_M1T(dispatch_fwd, p, x, preact, ds_out, X, planes, cmode, scale, st, false)
 }
 
 int launch_inv2d(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                  int cmode, float scale, int apply_gelu, cudaStream_t st) {
+  if (misaligned8(Y, addend, s_out, out)) { set_error("inv_transform: tensors must be 8-byte aligned"); return FNO_E_ARG; }
   FNO_DISPATCH_M1T(dispatch_inv, p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, false)
 }
 
@@ -456,19 +660,22 @@ static int setup_inv_attr(const Plan* p) {
 // plan will launch.  Called once from plan creation (not capture-time).
 int setup_transform2d_attrs(const Plan* pc) {
   Plan* p = const_cast<Plan*>(pc);
-  const size_t kMaxSmem = 200 * 1024;
+  const int tpp = p->W / pick_tn(p);
+  if (round_threads(tpp) > 1024) { set_error("W = %d too large (max %d)", p->W, 1024 * pick_tn(p)); return FNO_E_ARG; }
   auto pick = [&](bool fwd) {
-    // planes per CTA: best lane efficiency with <= 288 threads (3 CTAs/SM at <= 72 registers);
-    // wider CTAs only if a narrow one would idle more than 15 % of its lanes
+    // planes per CTA: best lane efficiency with <= 288 threads (2 resident CTAs per SM); wider
+    // CTAs only if a narrow one would idle more than 15 % of its lanes.  The shared-memory budget
+    // keeps two CTAs resident (<= 110 KB each) whenever a single plane allows it.
     int best = 1;
     double best_eff = 0.0;
-    for (int limit : {288, 576}) {
-      for (int G = 1; G <= 16; ++G) {
-        const int thr = round_threads(G * p->W);
+    for (int limit : {288, 448}) {
+      const size_t budget = (limit == 288) ? 110 * 1024 : 200 * 1024;
+      for (int G = 1; G <= 32; ++G) {
+        const int thr = round_threads(G * tpp);
         if (thr > limit) break;
         const size_t sm = fwd ? fwd_smem_bytes(p, G) : inv_smem_bytes(p, G);
-        if (sm > kMaxSmem) break;
-        const double eff = (double)(G * p->W) / thr;
+        if (sm > budget && G > 1) break;
+        const double eff = (double)(G * tpp) / thr;
         if (eff > best_eff + 0.02) { best_eff = eff; best = G; }
       }
       if (best_eff >= 0.85) break;
@@ -477,14 +684,13 @@ int setup_transform2d_attrs(const Plan* pc) {
     if (env != nullptr && std::atoi(env) > 0) {
       const int G = std::atoi(env);
       const size_t sm = fwd ? fwd_smem_bytes(p, G) : inv_smem_bytes(p, G);
-      if (round_threads(G * p->W) <= 1024 && sm <= kMaxSmem) best = G;
+      if (round_threads(G * tpp) <= 1024 && sm <= 200 * 1024) best = G;
     }
     return best;
   };
   p->G_fwd = pick(true);
   p->G_inv = pick(false);
-  if (round_threads(p->W) > 1024) { set_error("W = %d too large (max 1024)", p->W); return FNO_E_ARG; }
-  if (fwd_smem_bytes(p, p->G_fwd) > 227 * 1024 || inv_smem_bytes(p, p->G_inv) > 227 * 1024) {
+  if (fwd_smem_bytes(p, p->G_fwd) > kMaxOptinSmem || inv_smem_bytes(p, p->G_inv) > kMaxOptinSmem) {
     set_error("plane %dx%d with modes (%d,%d) needs too much shared memory", p->H, p->W, p->m1, p->m2);
     return FNO_E_ARG;
   }
