@@ -272,7 +272,7 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
     for (int kk = 0; kk < LB_ITEMS; ++kk) {
       const int item = slot + kk * LB_THREADS;
       if (item >= nitems) break;
-      const int c = item / FQ, fq = item - c * FQ;
+      const int fq = item / C, c = item - fq * C;   // lanes over channels: dh rows conflict-free, feature rows broadcast
       const float4* d4 = reinterpret_cast<const float4*>(dhs + c * TP);
       const float4* f0 = reinterpret_cast<const float4*>(fs + (4 * fq + 0) * TP);
       const float4* f1 = reinterpret_cast<const float4*>(fs + (4 * fq + 1) * TP);
@@ -295,7 +295,7 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
   for (int kk = 0; kk < LB_ITEMS; ++kk) {
     const int item = slot + kk * LB_THREADS;
     if (item >= nitems) break;
-    const int c = item / FQ, fq = item - c * FQ;
+    const int fq = item / C, c = item - fq * C;   // lanes over channels: dh rows conflict-free, feature rows broadcast
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       if (4 * fq + q <= F) pp[(size_t)c * (F + 1) + 4 * fq + q] = acc[kk][q];

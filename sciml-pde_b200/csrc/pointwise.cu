@@ -294,7 +294,9 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
 // over pixel quads (LDS.128: 2T loads per 4 T^2 FMA).  Nothing but the bulk copies touches global
 // memory in the steady state, so the kernel streams at the HBM rate set by its 8 bytes/pixel/channel.
 // ------------------------------------------------------------------------------------------
-constexpr int WG2_STAGES = 4;
+constexpr int WG2_STAGES = 2;
+constexpr int WG2_KT = 512;      // pixels per slab: 2 KB per bulk copy (the TMA unit retires ~1 copy / 46 cycles / SM,
+                                 // so 512-byte copies cap the stream at ~3 TB/s -- profiles/r1_d)
 constexpr int WG2_MAXW = 8;      // consumer warps per CTA
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -334,10 +336,11 @@ template <int T>
 __global__ void __launch_bounds__(32 * (WG2_MAXW + 1))
 wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co,
                       int Ci, long N, int slabs_per_sample, long total_slabs, long slabs_per_cta, int tiles_i,
-                      int ntiles, int nwarps) {
+                      int ntiles, int nwarps, int KH) {
   extern __shared__ __align__(16) float sm[];   // WG2_STAGES x ([Co][KT] ds slab, [Ci][KT] a slab), then barriers
+  constexpr int KT2 = WG2_KT;
   const int rows = Co + Ci;
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)WG2_STAGES * rows * KT);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)WG2_STAGES * rows * KT2);
   unsigned long long* empty = full + WG2_STAGES;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -361,22 +364,23 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
       const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
       mbar_wait(empty + stage, ph ^ 1u);
       const long b = slab / slabs_per_sample;
-      const long k0 = (slab - b * slabs_per_sample) * KT;
+      const long k0 = (slab - b * slabs_per_sample) * KT2;
       const long left = N - k0;
-      const unsigned bytes = (unsigned)((left < KT ? left : KT) * sizeof(float));
-      float* dst = sm + (size_t)stage * rows * KT;
+      const unsigned bytes = (unsigned)((left < KT2 ? left : KT2) * sizeof(float));
+      float* dst = sm + (size_t)stage * rows * KT2;
       if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes * (unsigned)rows);
       __syncwarp();
       for (int c = lane; c < rows; c += 32) {
         const float* src = (c < Co) ? (ds + ((size_t)b * Co + c) * N + k0) : (a + ((size_t)b * Ci + (c - Co)) * N + k0);
-        bulk_g2s(dst + (size_t)c * KT, src, bytes, full + stage);
+        bulk_g2s(dst + (size_t)c * KT2, src, bytes, full + stage);
       }
     }
     return;
   }
 
-  // ---- consumer warps: one T x T tile each -------------------------------------------------
-  const int tile = blockIdx.y * nwarps + warp;
+  // ---- consumer warps: (tile, pixel part) each; a tile is a T x T block of outputs ------------
+  const int kh = warp % KH;                       // which 1/KH of the slab's pixels
+  const int tile = blockIdx.y * (nwarps / KH) + warp / KH;
   const bool has_tile = tile < ntiles;
   const int to = has_tile ? (tile / tiles_i) * T : 0;
   const int ti = has_tile ? (tile % tiles_i) * T : 0;
@@ -389,35 +393,39 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
 #pragma unroll
     for (int c = 0; c < T; ++c) acc[r][c] = 0.f;
   }
+  const int steps = KT2 / 128;                    // 128 pixels (32 lanes x 4) per step
   for (long slab = s_begin; slab < s_end; ++slab) {
     const int it = (int)(slab - s_begin);
     const int stage = it % WG2_STAGES;
     const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
     mbar_wait(full + stage, ph);
     const long b = slab / slabs_per_sample;
-    const long left = N - (slab - b * slabs_per_sample) * KT;
-    // pixel quad of this lane; a slab at the end of a sample is short by whole quads (N % 4 == 0)
-    if (has_tile && 4 * lane < left) {
-      const float* ds_s = sm + (size_t)stage * rows * KT + 4 * lane;
-      const float* a_s = ds_s + (size_t)Co * KT;
-      float4 dv[T];
+    const long left = N - (slab - b * slabs_per_sample) * KT2;
+    if (has_tile) {
+      for (int st = kh; st < steps; st += KH) {
+        const int px = st * 128 + 4 * lane;       // a short slab at the end of a sample ends on a quad (N % 4 == 0)
+        if (px >= left) break;
+        const float* ds_s = sm + (size_t)stage * rows * KT2 + px;
+        const float* a_s = ds_s + (size_t)Co * KT2;
+        float4 dv[T];
 #pragma unroll
-      for (int r = 0; r < T; ++r)
-        dv[r] = (to + r < Co) ? *reinterpret_cast<const float4*>(ds_s + (to + r) * KT) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias_tile) {
+        for (int r = 0; r < T; ++r)
+          dv[r] = (to + r < Co) ? *reinterpret_cast<const float4*>(ds_s + (to + r) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias_tile) {
 #pragma unroll
-        for (int r = 0; r < T; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
-      }
+          for (int r = 0; r < T; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
+        }
 #pragma unroll
-      for (int c = 0; c < T; ++c) {
-        const float4 av =
-            (ti + c < Ci) ? *reinterpret_cast<const float4*>(a_s + (ti + c) * KT) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < T; ++c) {
+          const float4 av =
+              (ti + c < Ci) ? *reinterpret_cast<const float4*>(a_s + (ti + c) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int r = 0; r < T; ++r) {
-          acc[r][c] = fmaf(dv[r].x, av.x, acc[r][c]);
-          acc[r][c] = fmaf(dv[r].y, av.y, acc[r][c]);
-          acc[r][c] = fmaf(dv[r].z, av.z, acc[r][c]);
-          acc[r][c] = fmaf(dv[r].w, av.w, acc[r][c]);
+          for (int r = 0; r < T; ++r) {
+            acc[r][c] = fmaf(dv[r].x, av.x, acc[r][c]);
+            acc[r][c] = fmaf(dv[r].y, av.y, acc[r][c]);
+            acc[r][c] = fmaf(dv[r].z, av.z, acc[r][c]);
+            acc[r][c] = fmaf(dv[r].w, av.w, acc[r][c]);
+          }
         }
       }
     }
@@ -425,7 +433,8 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
     if (lane == 0) mbar_arrive(empty + stage);
   }
   if (!has_tile) return;
-  float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
+  // part[(cta * KH + kh)][Co][Ci + 1]
+  float* __restrict__ pp = part + ((size_t)blockIdx.x * KH + kh) * Co * (Ci + 1);
 #pragma unroll
   for (int r = 0; r < T; ++r) {
 #pragma unroll
@@ -536,8 +545,9 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
   const int aligned = (N % 4 == 0) && ((reinterpret_cast<size_t>(ds) | reinterpret_cast<size_t>(a)) % 16 == 0);
   float* part = static_cast<float*>(work);
   dim3 grid((unsigned)ctas, ygroups);
-  const size_t smem2 = sizeof(float) * (size_t)WG2_STAGES * (Co + Ci) * KT + 2 * WG2_STAGES * sizeof(unsigned long long);
-  if (aligned && smem2 <= 200 * 1024) {
+  // v2 (TMA bulk-fed): persistent CTAs, one per SM, each over a contiguous range of 512-pixel slabs
+  const size_t smem2 = sizeof(float) * (size_t)WG2_STAGES * (Co + Ci) * WG2_KT + 2 * WG2_STAGES * sizeof(unsigned long long);
+  if (aligned && smem2 <= 200 * 1024 && ntiles <= WG2_MAXW) {
     static std::atomic<int> attr2_done{0};
     if (!attr2_done.load()) {
       if (cudaFuncSetAttribute(wgrad2_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
@@ -545,13 +555,20 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
         return check_launch("cudaFuncSetAttribute(wgrad2)");
       attr2_done.store(1);
     }
-    wgrad2_partial_kernel<T><<<grid, 32 * (warps + 1), smem2, st>>>(ds, a, part, Co, Ci, N, slabs_per_sample, total_slabs,
-                                                                    spc, tiles_i, ntiles, warps);
+    const int KH = (2 * ntiles <= WG2_MAXW) ? 2 : 1;       // pixel halves per tile
+    const int warps2 = ntiles * KH;
+    const int sps2 = (int)((N + WG2_KT - 1) / WG2_KT);
+    const long total2s = (long)B * sps2;
+    long ctas2 = total2s < 148 ? total2s : 148;
+    const long spc2 = (total2s + ctas2 - 1) / ctas2;
+    ctas2 = (total2s + spc2 - 1) / spc2;
+    wgrad2_partial_kernel<T><<<dim3((unsigned)ctas2, 1), 32 * (warps2 + 1), smem2, st>>>(
+        ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH);
     count_launch();
     int rc2 = check_launch("wgrad2_partial_kernel");
     if (rc2 != FNO_OK) return rc2;
     const int total2 = Co * (Ci + 1);
-    wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas, Co, Ci);
+    wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas2 * KH, Co, Ci);
     count_launch();
     return check_launch("wgrad_reduce_kernel");
   }
