@@ -62,6 +62,11 @@ struct Vec<2> {
   __device__ __forceinline__ void st(float* p) const { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
 };
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+constexpr int PF_DIST = 16;   // row pairs of look-ahead for the L2 prefetches of the column passes
+
 template <int JP>
 __device__ __forceinline__ void load_row(float (&tw)[JP], const float* __restrict__ row) {
   const float4* r4 = reinterpret_cast<const float4*>(row);
@@ -173,11 +178,25 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
       fold_accumulate_even<M1T, TN>(acc, twH_s, load1(0));
       const int npairs = (H - 1) / 2;
       // PG row pairs per step: all loads of a step are issued before the FMAs that consume them
-      // (memory-level parallelism per thread; the resident warps provide the rest)
+      // (memory-level parallelism per thread; the resident warps provide the rest).  A software
+      // pipeline (loads of group g+1 before the FMAs of group g) was measured slower (0.109 vs
+      // 0.101 ms at cfg 1): the burst form keeps more bytes in flight per thread.
       constexpr int PG = PREMUL ? 2 : 4;
       int t = 1;
       for (; t + PG - 1 <= npairs; t += PG) {
         Vec<TN> v1[PG], v2[PG], s1[PG], s2[PG];
+        // pull the rows PF_DIST pairs ahead into L2: the loads below then pay the L2 latency, not HBM's
+        if (t + PF_DIST + PG - 1 <= npairs) {
+#pragma unroll
+          for (int u = 0; u < PG; ++u) {
+            prefetch_l2(xp + (t + PF_DIST + u) * W);
+            prefetch_l2(xp + (H - t - PF_DIST - u) * W);
+            if (PREMUL) {
+              prefetch_l2(sp + (t + PF_DIST + u) * W);
+              prefetch_l2(sp + (H - t - PF_DIST - u) * W);
+            }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < PG; ++u) {
           v1[u] = Vec<TN>::ld(xp + (t + u) * W);
@@ -470,6 +489,13 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
   for (; t + PG - 1 <= npairs; t += PG) {
     Vec<TN> n1[PG], n2[PG];
     const bool more = (t + 2 * PG - 1 <= npairs);
+    if (has_add && t + PF_DIST + PG - 1 <= npairs) {
+#pragma unroll
+      for (int u = 0; u < PG; ++u) {
+        prefetch_l2(ap + (t + PF_DIST + u) * W);
+        prefetch_l2(ap + (H - t - PF_DIST - u) * W);
+      }
+    }
 #pragma unroll
     for (int u = 0; u < PG; ++u) {
       if (more) { n1[u] = ld_add(t + PG + u); n2[u] = ld_add(H - t - PG - u); }
@@ -529,7 +555,7 @@ inline int pick_tn(const Plan* p) { return ((p->W & 1) == 0 && p->M1T <= 16) ? 2
 
 template <int M1T, int TN, int MAXT, int MINB>
 int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
-                 int cmode, float scale, cudaStream_t st, int threads, size_t smem, bool attr_only) {
+                 int cmode, float scale, cudaStream_t st, int threads, size_t smem, bool attr_only, int G_launch) {
   auto k0 = fwd2d_kernel<M1T, TN, false, MAXT, MINB>;
   auto k1 = fwd2d_kernel<M1T, TN, true, MAXT, MINB>;
   if (attr_only) {
@@ -538,7 +564,7 @@ int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_o
       return check_launch("cudaFuncSetAttribute(fwd2d)");
     return FNO_OK;
   }
-  const int G = p->G_fwd;
+  const int G = G_launch;
   const unsigned grid = (unsigned)((planes + G - 1) / G);
   if (preact != nullptr)
     k1<<<grid, threads, smem, st>>>(x, preact, ds_out, reinterpret_cast<float2*>(X), p->twH, p->twW, p->H,
@@ -553,14 +579,14 @@ int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_o
 template <int M1T, int TN, int MAXT, int MINB>
 int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                  int cmode, float scale, int apply_gelu, cudaStream_t st, int threads, size_t smem,
-                 bool attr_only) {
+                 bool attr_only, int G_launch) {
   auto k = inv2d_kernel<M1T, TN, MAXT, MINB>;
   if (attr_only) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(inv2d)");
     return FNO_OK;
   }
-  const int G = p->G_inv;
+  const int G = G_launch;
   const unsigned grid = (unsigned)((planes + G - 1) / G);
   k<<<grid, threads, smem, st>>>(reinterpret_cast<const float2*>(Y), addend, s_out, out, p->twH, p->twW, p->H,
                                  p->W, p->WP, p->m1, p->m2, G, planes, cmode, scale, apply_gelu);
@@ -570,33 +596,65 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
 
 inline int round_threads(int n) { return (n + 31) & ~31; }
 constexpr size_t kMaxOptinSmem = 227 * 1024;  // sm_100: 232448 B opt-in per CTA
+constexpr int kSMs = 148;
+
+// Planes per CTA for this launch.  The plan's G maximises lane efficiency; with `planes` known the
+// choice also has to avoid a nearly empty last wave: a launch of n CTAs on 148 * cps resident slots
+// takes ceil(n / slots) rounds of (cps * G) planes per SM, e.g. 2560 planes (cfg 1, batch 128):
+// G = 4 -> 2 CTAs/SM, 640 CTAs = 2.16 waves = 3 rounds of 8 planes; G = 3 -> 3 CTAs/SM, 854 CTAs
+// = 1.92 waves = 2 rounds of 9 planes.  Only the <= 288-thread class (96 registers) is searched.
+inline int pick_planes_per_cta(const Plan* p, long planes, bool fwd, int tpp, int G_plan) {
+  if (round_threads(G_plan * tpp) > 288) return G_plan;
+  int best = G_plan;
+  double best_cost = 1e30;
+  for (int G = 1; G <= 16; ++G) {
+    const int thr = round_threads(G * tpp);
+    if (thr > 288) break;
+    const size_t sm = (fwd ? fwd_smem_bytes(p, G) : inv_smem_bytes(p, G)) + 1024;
+    if (sm > 113 * 1024) break;
+    long cps = 65536 / (96 * thr);
+    if ((long)(kMaxOptinSmem / sm) < cps) cps = (long)(kMaxOptinSmem / sm);
+    if (2048 / thr < cps) cps = 2048 / thr;
+    if (cps < 1) cps = 1;
+    const long ctas = (planes + G - 1) / G;
+    const long rounds = (ctas + kSMs * cps - 1) / (kSMs * cps);
+    // time ~ rounds x (lanes issued per SM per round); idle lanes of a ragged CTA still cost issue slots
+    const double cost = (double)rounds * cps * thr * (cps * thr >= 512 ? 1.0 : 1.25);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = G; }
+  }
+  return best;
+}
 
 // launch-bound classes: <= 288 threads with 2 resident CTAs (<= 112 registers), <= 448 threads
 // alone on the SM (<= 144 registers), wider CTAs (very wide planes) at 64 registers
 template <int M1T, int TN>
 int dispatch_fwd_tn(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
                     int cmode, float scale, cudaStream_t st, bool attr_only) {
-  const int threads = round_threads(p->G_fwd * (p->W / TN));
+  const int tpp = p->W / TN;
+  const int G = attr_only ? p->G_fwd : pick_planes_per_cta(p, planes, true, tpp, p->G_fwd);
+  const int threads = round_threads(G * tpp);
   // attr_only: opt every instantiation this plan can reach into the device maximum once; the
   // limit is per kernel function, so it must never be lowered by a later, smaller plan
-  const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, p->G_fwd);
+  const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, G);
   if (threads <= 288)
-    return launch_fwd_t<M1T, TN, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+    return launch_fwd_t<M1T, TN, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only, G);
   if (threads <= 448)
-    return launch_fwd_t<M1T, TN, 448, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
-  return launch_fwd_t<M1T, TN, 1024, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only);
+    return launch_fwd_t<M1T, TN, 448, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only, G);
+  return launch_fwd_t<M1T, TN, 1024, 1>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only, G);
 }
 
 template <int M1T, int TN>
 int dispatch_inv_tn(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,
                     int cmode, float scale, int apply_gelu, cudaStream_t st, bool attr_only) {
-  const int threads = round_threads(p->G_inv * (p->W / TN));
-  const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, p->G_inv);
+  const int tpp = p->W / TN;
+  const int G = attr_only ? p->G_inv : pick_planes_per_cta(p, planes, false, tpp, p->G_inv);
+  const int threads = round_threads(G * tpp);
+  const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, G);
   if (threads <= 288)
-    return launch_inv_t<M1T, TN, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+    return launch_inv_t<M1T, TN, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only, G);
   if (threads <= 448)
-    return launch_inv_t<M1T, TN, 448, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
-  return launch_inv_t<M1T, TN, 1024, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only);
+    return launch_inv_t<M1T, TN, 448, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only, G);
+  return launch_inv_t<M1T, TN, 1024, 1>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only, G);
 }
 
 template <int M1T>
