@@ -53,6 +53,9 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tail", default="graph", choices=["torch", "fused", "graph"],
+                    help="step tail: torch library ops / fused device-side tail / fused + whole step in one CUDA graph "
+                         "(graph applies to single-GPU runs; data-parallel runs use the fused eager tail)")
     return ap.parse_args()
 
 
@@ -251,7 +254,7 @@ def run_ours(args):
     from fno_b200 import data, lib
     from fno_b200.dp import BucketedGradAllReduce
     from fno_b200.fno import FNO2d
-    from fno_b200.train import TrainStep
+    from fno_b200.train import FusedTrainStep, TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -267,10 +270,17 @@ def run_ours(args):
 
     torch.manual_seed(16)
     model = FNO2d(**CFG).to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
-    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100000)
     dp = BucketedGradAllReduce(model) if world > 1 else None
-    step = TrainStep(model, opt, sched, dp=dp)
+    if args.tail == "torch":
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
+        sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=100000)
+        step = TrainStep(model, opt, sched, dp=dp)
+        eager_step = step
+    else:
+        step = FusedTrainStep(model, lr=1e-3, weight_decay=1e-4, t_max=100000, dp=dp,
+                              graph=(args.tail == "graph" and world == 1))
+        eager_step = step._eager
+    graphed = args.tail == "graph" and world == 1
 
     # two distinct host batches per rank (pinned); device copies for the HBM-resident measurement
     host = []
@@ -293,7 +303,10 @@ def run_ours(args):
         return float(t.item())
 
     # ---- device-resident throughput ---------------------------------------------------------
-    for i in range(W):
+    l0 = lib.launch_count()
+    eager_step(*devb[0])                      # also counts this library's launches per (eager) step
+    launches_per_step = lib.launch_count() - l0
+    for i in range(max(W, 3)):                # graph mode: calls 1-2 eager, call 3 captures
         step(*devb[i % 2])
     barrier()
     sampler = ClockSampler(local)
@@ -306,7 +319,7 @@ def run_ours(args):
         loss = step(*devb[i % 2])
     e1.record()
     torch.cuda.synchronize()
-    launches = lib.launch_count() - l0
+    launches = (lib.launch_count() - l0) if not graphed else launches_per_step * K   # replays do not pass the counter
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -368,7 +381,7 @@ def run_ours(args):
     nprof = min(K, 5)
     with KernelTimer(lib) as kt:
         for i in range(nprof):
-            step(*devb[i % 2])
+            eager_step(*devb[i % 2])
         ksum = kt.summary()
     barrier()
     if rank == 0:
@@ -403,6 +416,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
                    "parallelism": f"dp{world}" if world > 1 else "single",
+                   "step_tail": args.tail if (world == 1 or args.tail == "torch") else "fused",
                    "l2_policy": f"inputs larger than L2: two alternating {h2d_bytes / 1e6:.0f} MB input batches, "
                                 f"{4 * CFG['width'] * (RES + 2) ** 2 * B / 1e6:.0f} MB per activation tensor"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

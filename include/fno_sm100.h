@@ -156,6 +156,30 @@ int fno_head_bwd(const float* h, const float* dout, const float* W1, const float
                  void* work, int B, int R_in, int W_in, int R_out, int Wp, int C, int HID, int V,
                  fno_stream_t stream);
 
+/* ---- step tail: loss, gradient clipping, Adam, LR schedule --------------------- */
+/* nrmse(out, target).mean() of fno/train.py:34-40,:266-267 for out / target [B, P, V] (P = pixels x
+ * output steps): loss[0] = mean_{b,v} ( mean_p (out-y)^2 / (1e-7 + mean_p y^2) ).
+ * work: fno_nrmse_workspace_bytes(B, V) bytes, kept for the backward call.                          */
+size_t fno_nrmse_workspace_bytes(int B, int V);
+int fno_nrmse_fwd(const float* out, const float* target, float* loss, void* work, int B, long P,
+                  int V, fno_stream_t stream);
+/* dout = gscale[0] * d loss / d out (gscale: device scalar, NULL = 1).                              */
+int fno_nrmse_bwd(const float* out, const float* target, const void* work, const float* gscale,
+                  float* dout, int B, long P, int V, fno_stream_t stream);
+/* fno/train.py:251-259,:273-278 without the host round trip: total_norm over all chunks,
+ * clip_value = max(hparams[7], hparams[8] * total_norm), clip_grad_norm_ coefficient, then
+ * Adam with coupled L2 weight decay and (if hparams[2] = T_max > 0) the CosineAnnealingLR value of
+ * this step, all driven by the device-resident step counter state[0].
+ *   chunks   device array of { float* p; const float* g; float* m; float* v; int n; int pad; }
+ *            (fno_opt_chunk_bytes() each, n <= fno_opt_chunk_floats()); complex tensors as real pairs
+ *   partials device scratch, nchunks floats
+ *   state    device float[8]: step, total_norm, clip_coef, lr, 1-beta1^t, 1-beta2^t, clip_value, clipped_norm
+ *   hparams  device float[9]: lr0, eta_min, T_max, beta1, beta2, eps, weight_decay, clip_floor, clip_frac */
+int fno_opt_chunk_floats(void);
+size_t fno_opt_chunk_bytes(void);
+int fno_clip_adam_step(const void* chunks, int nchunks, float* partials, float* state,
+                       const float* hparams, fno_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,9 +43,10 @@ class _Bucket:
         self.params = list(params)
         dev = self.params[0].device
         sizes = [_real_view(p).numel() for p in self.params]
-        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        padded = [(n + 3) & ~3 for n in sizes]          # 16-byte aligned slots (complex views need even offsets)
+        self.flat = torch.zeros(sum(padded), dtype=torch.float32, device=dev)
         off = 0
-        for p, n in zip(self.params, sizes):
+        for p, n, npad in zip(self.params, sizes, padded):
             chunk = self.flat[off:off + n]
             if p.is_complex():
                 view = torch.view_as_complex(chunk.view(*p.shape, 2))
@@ -54,7 +55,7 @@ class _Bucket:
             if p.grad is not None:
                 view.copy_(p.grad)
             p.grad = view
-            off += n
+            off += npad
         self.pending = len(self.params)
         self.work = None
 

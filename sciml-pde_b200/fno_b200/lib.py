@@ -71,6 +71,12 @@ def load():
             "fno_head_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
             "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
             "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
+            "fno_nrmse_workspace_bytes": (C.c_size_t, [i, i]),
+            "fno_nrmse_fwd": (i, [vp, vp, vp, vp, i, l, i, vp]),
+            "fno_nrmse_bwd": (i, [vp, vp, vp, vp, vp, i, l, i, vp]),
+            "fno_opt_chunk_floats": (i, []),
+            "fno_opt_chunk_bytes": (C.c_size_t, []),
+            "fno_clip_adam_step": (i, [vp, i, vp, vp, vp, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(lib, name)
@@ -88,6 +94,8 @@ EXPORTED_SYMBOLS = (
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
     "fno_lift_bwd", "fno_head_fwd", "fno_head_bwd_workspace_bytes", "fno_head_bwd",
+    "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
+    "fno_opt_chunk_bytes", "fno_clip_adam_step",
 )
 
 
