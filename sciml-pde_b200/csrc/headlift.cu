@@ -472,7 +472,7 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
   for (int v = 0; v < VP; ++v) aw2[v] = 0.f;
 
   // inputs of one tile for this thread's pixel: h[0..C), dout * std
-  float hv[CP], dv[VP];
+  float hv[CP], dv[VP], sv[VP];     // dv * sv is formed at the start of phase A, not here: the prefetch must not wait
   auto load_tile = [&](int tile) {
     int b, r, w0;
     decode_tile(tm, g, tile, b, r, w0);
@@ -484,7 +484,10 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
 #pragma unroll
     for (int c = 0; c < CP; ++c) hv[c] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
 #pragma unroll
-    for (int v = 0; v < VP; ++v) dv[v] = (valid && v < V) ? __ldg(op + v) * __ldg(sd + v) : 0.f;
+    for (int v = 0; v < VP; ++v) {
+      dv[v] = (valid && v < V) ? __ldg(op + v) : 0.f;
+      sv[v] = (v < V) ? __ldg(sd + v) : 0.f;
+    }
   };
   if ((int)blockIdx.x < tm.total) load_tile(blockIdx.x);
 
@@ -495,6 +498,8 @@ head_bwd_kernel(const float* __restrict__ h, const float* __restrict__ dout, con
     float dacc[CP];
 #pragma unroll
     for (int c = 0; c < CP; ++c) dacc[c] = 0.f;
+#pragma unroll
+    for (int v = 0; v < VP; ++v) dv[v] *= sv[v];
     if (jq == 0) {
 #pragma unroll
       for (int c = 0; c < CP; ++c) hs[c * TP + pix] = hv[c];

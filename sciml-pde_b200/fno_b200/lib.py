@@ -314,18 +314,26 @@ def pointwise_fwd(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
     return out
 
 
-def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True):
+def pointwise_wgrad_buffers(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True):
+    """Allocates (gw, gb, work) for pointwise_wgrad on the CURRENT stream (so that the launch itself
+    may run on a side stream without handing the caching allocator cross-stream blocks)."""
+    B, Co, Ci = ds.shape[0], ds.shape[1], a.shape[1]
+    N = ds.numel() // (B * Co)
+    nbytes = load().fno_pointwise_wgrad_workspace_bytes(B, Co, Ci, N)
+    work = torch.empty(nbytes // 4, dtype=torch.float32, device=ds.device)
+    gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=ds.device)
+    gb = torch.empty(Co, dtype=torch.float32, device=ds.device) if need_bias else None
+    return gw, gb, work
+
+
+def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True, buffers=None):
     _require(ds, torch.float32, "ds")
     _require(a, torch.float32, "a")
     B, Co, Ci = ds.shape[0], ds.shape[1], a.shape[1]
     N = ds.numel() // (B * Co)
-    lib = load()
-    nbytes = lib.fno_pointwise_wgrad_workspace_bytes(B, Co, Ci, N)
-    work = torch.empty(nbytes // 4, dtype=torch.float32, device=ds.device)
-    gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=ds.device)
-    gb = torch.empty(Co, dtype=torch.float32, device=ds.device) if need_bias else None
-    rc = lib.fno_pointwise_wgrad(ds.data_ptr(), a.data_ptr(), gw.data_ptr(), _ptr(gb), work.data_ptr(), B, Co, Ci, N,
-                                 _stream())
+    gw, gb, work = buffers if buffers is not None else pointwise_wgrad_buffers(ds, a, weight_shape, need_bias=need_bias)
+    rc = load().fno_pointwise_wgrad(ds.data_ptr(), a.data_ptr(), gw.data_ptr(), _ptr(gb), work.data_ptr(), B, Co, Ci, N,
+                                    _stream())
     _check(rc, "fno_pointwise_wgrad")
     return gw, gb
 
