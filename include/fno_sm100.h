@@ -147,6 +147,11 @@ int fno_lift_bwd(const float* x, const float* grid, const float* stats, const fl
 int fno_head_fwd(const float* h, const float* W1, const float* b1, const float* W2, const float* b2,
                  const float* stats, float* out, int B, int R_in, int W_in, int R_out, int Wp, int C,
                  int HID, int V, fno_stream_t stream);
+/* Same contract on the tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM) with a 3xTF32
+ * split so that the result stays within fp32-mode tolerance; requires HID = 128, C <= 32, V <= 4.  */
+int fno_head_fwd_tc(const float* h, const float* W1, const float* b1, const float* W2,
+                    const float* b2, const float* stats, float* out, int B, int R_in, int W_in,
+                    int R_out, int Wp, int C, int HID, int V, fno_stream_t stream);
 /* backward: dout [B, R_in*W_in, V] -> dh [B, C, R_out, Wp] (zero in the padding), gW1, gb1, gW2,
  * gb2; the hidden layer is recomputed.  HID must be a multiple of 8, <= 128 (the reference
  * hard-codes 128).  work: fno_head_bwd_workspace_bytes(C, HID, V) bytes.                           */

@@ -1,0 +1,302 @@
+// Projection head on the 5th-generation tensor cores (tcgen05 + TMEM), fp32-accurate through a
+// 3xTF32 split.
+//
+// The head (fno/fno.py:180-187) is the one genuinely dense contraction of the width-20 model: per
+// pixel  pre[128] = W1[128 x C] h[C] + b1,  out[V] = W2 gelu(pre) + b2  -- 2 816 FMA per pixel forward,
+// ~8 300 backward, half of all FMAs of a training step, and the FP32 path is bound by instruction
+// issue.  Here the C -> 128 product runs as  D[128 pixels x 128 hidden] =
+// A[128 x K] B[K x 128]  with tcgen05.mma.kind::tf32, accumulators in TMEM, and the CUDA cores keep
+// only the element-wise part (bias, exact-erf GELU, the 128 -> V product).
+//
+// fp32 mode (<= 1e-5 relative, BASELINE north_star) rules out single-pass TF32 (6e-4): every operand
+// is split x = hi + lo, hi = rna_tf32(x), and three MMAs accumulate lo*hi + hi*lo + hi*hi into the
+// same TMEM tile (the dropped lo*lo term is 2^-22 relative).
+//
+// Operand staging (no-swizzle canonical layout, 8 x 16-byte core matrices, both operands K-major --
+// tools/ubench/umma_probe.cu verified this layout on the hardware and found that kind::tf32 with an
+// MN-major operand returns zeros, so the channel-first activation is transposed on the way in):
+// thread = pixel loads its channels (coalesced across the warp: 32 consecutive pixels per channel
+// row), splits them in registers and stores four channels per 16-byte chunk
+//     A[m = pixel ][k = channel]: (m % 8) * 16 + (m / 8) * 1024 + (k / 4) * 128 + (k % 4) * 4   bytes
+//     B[n = hidden][k = channel]: (n % 8) * 16 + (n / 8) * 1024 + (k / 4) * 128 + (k % 4) * 4   bytes
+// (W1 is staged once per CTA); LBO = 128 B between the 16-byte K chunks, SBO = 1024 B between 8-row groups.
+#include "common.cuh"
+
+namespace fno {
+namespace {
+
+constexpr int TC_M = 128;          // pixels per tile = TMEM lanes
+constexpr int TC_HID = 128;        // hidden units = accumulator columns
+constexpr int TC_KP = 32;          // channel padding of the staged operands (4 core-matrix groups of 8)
+constexpr int TC_EPI_WARPS = 8;    // loader / epilogue warps: 4 lane quadrants x 2 column halves
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1);   // + 1 MMA-issue warp
+constexpr int TC_VP = 4;
+
+struct HeadGeo {
+  int R_in, W_in, R_out, Wp;
+  long npix, plane;
+};
+
+// ---- tcgen05 wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(unsigned* smem_dst, unsigned ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned taddr, unsigned ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                            unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane of its warp's quadrant)
+__device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
+  unsigned r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 in bits [0,14),
+// leading-dimension byte offset >> 4 in [16,30), stride-dimension byte offset >> 4 in [32,46),
+// version = 1 in [46,48), layout_type = SWIZZLE_NONE (0) in [61,64)
+__device__ __forceinline__ unsigned long long umma_desc(const void* smem, unsigned lbo_bytes, unsigned sbo_bytes) {
+  const unsigned long long addr = (smem_u32(smem) & 0x3FFFFu) >> 4;
+  return addr | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((unsigned long long)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor for kind::tf32 (cute::UMMA::InstrDescriptor): c_format = F32 (1) at [4,6),
+// a_format = b_format = TF32 (2) at [7,10) / [10,13), a_major at 15, b_major at 16 (0 = K-major,
+// 1 = MN-major), N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)a_mn_major << 15) | ((unsigned)b_mn_major << 16) |
+         ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  unsigned h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  lo = x - hi;
+}
+
+// byte offsets inside the staged operand buffers (see the file header)
+__device__ __forceinline__ int b_off_bytes(int n, int k) { return (n & 7) * 16 + (n >> 3) * 1024 + (k >> 2) * 128 + (k & 3) * 4; }
+
+constexpr int A_BYTES = 16 * 1024;    // [16 pixel groups ][8 channel chunks][8][4] floats
+constexpr int B_BYTES = 16 * 1024;    // [16 hidden groups][8 channel chunks][8][4] floats
+
+// ------------------------------------------------------------------------------------------
+// forward:  out = (W2 gelu(W1 h + b1) + b2) * std + mean
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
+                   const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
+                   float* __restrict__ out, HeadGeo g, int C, int V, int tiles_per_sample, int total_tiles) {
+  extern __shared__ __align__(128) unsigned char tsm[];
+  unsigned char* a_hi = tsm;                       // A_BYTES
+  unsigned char* a_lo = a_hi + A_BYTES;
+  unsigned char* w_hi = a_lo + A_BYTES;            // B_BYTES
+  unsigned char* w_lo = w_hi + B_BYTES;
+  float* W2s = reinterpret_cast<float*>(w_lo + B_BYTES);   // [HID][VP]
+  float* b1s = W2s + TC_HID * TC_VP;                       // [HID]
+  float* ox = b1s + TC_HID;                                // [TC_M][VP] partial outputs of the upper column half
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ox + TC_M * TC_VP);   // a_ready, d_full, d_free
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  unsigned long long* a_ready = bars;
+  unsigned long long* d_full = bars + 1;
+  unsigned long long* d_free = bars + 2;
+  if (tid == 0) {
+    mbar_init(a_ready, TC_EPI_WARPS);
+    mbar_init(d_full, 1);
+    mbar_init(d_free, TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 128);
+  // stage W1 (hi / lo, K-major B operand, zero padded to TC_KP channels), W2^T, b1
+  for (int i = tid; i < TC_HID * TC_KP; i += TC_THREADS) {
+    const int n = i / TC_KP, k = i - n * TC_KP;
+    float hi = 0.f, lo = 0.f;
+    if (k < C) split_tf32(__ldg(W1 + (size_t)n * C + k), hi, lo);
+    *reinterpret_cast<float*>(w_hi + b_off_bytes(n, k)) = hi;
+    *reinterpret_cast<float*>(w_lo + b_off_bytes(n, k)) = lo;
+  }
+  for (int i = tid; i < TC_HID * TC_VP; i += TC_THREADS) {
+    const int j = i / TC_VP, v = i - j * TC_VP;
+    W2s[i] = (v < V) ? __ldg(W2 + (size_t)v * TC_HID + j) : 0.f;
+  }
+  for (int i = tid; i < TC_HID; i += TC_THREADS) b1s[i] = __ldg(b1 + i);
+  // zero the A buffers once: channel rows >= C are never written again
+  for (int i = tid; i < 2 * A_BYTES / 16; i += TC_THREADS) reinterpret_cast<float4*>(a_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const int ksteps = (C + 7) / 8;
+
+  if (warp == TC_EPI_WARPS) {
+    // ---- MMA issuer -------------------------------------------------------------------------------
+    constexpr unsigned idesc = umma_idesc_tf32(TC_M, TC_HID, /*A K-major*/ 0, /*B K-major*/ 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(a_ready, (unsigned)it & 1u);
+      mbar_wait(d_free, ((unsigned)it & 1u) ^ 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        unsigned acc = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi
+          const unsigned char* A = (pass == 0) ? a_lo : a_hi;
+          const unsigned char* Bm = (pass == 1) ? w_lo : w_hi;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            // K = 8 per instruction = two 16-byte chunks: +256 B per K step for both operands
+            tc_mma_tf32(tmem_base, umma_desc(A + ks * 256, 128, 1024), umma_desc(Bm + ks * 256, 128, 1024), idesc, acc);
+            acc = 1;
+          }
+        }
+        tc_commit(d_full);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- loader / epilogue warps ------------------------------------------------------------------
+    const int quad = warp & 3;                     // TMEM lane quadrant of this warp
+    const int half = warp >> 2;                    // column half: hidden units [64 * half, 64 * half + 64)
+    const int m = quad * 32 + lane;                // pixel of the tile owned in the epilogue
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_per_sample;
+      const long p0 = (long)(tile - b * tiles_per_sample) * TC_M;
+      // -- stage the activation tile: thread = (pixel, chunk parity); 4 channels per 16-byte chunk
+      if (it > 0) mbar_wait(d_full, (unsigned)(it - 1) & 1u);   // previous tile's MMAs have consumed A
+      {
+        const int pm = tid & (TC_M - 1);           // pixel of the tile staged by this thread
+        const long p = p0 + pm;
+        const bool valid = p < g.npix;
+        const long r = valid ? p / g.W_in : 0;
+        const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+        const int abase = (pm & 7) * 16 + (pm >> 3) * 1024;
+        for (int kc = tid >> 7; kc < 2 * ksteps; kc += 2) {
+          float x4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = 4 * kc + e;
+            x4[e] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+          }
+          float hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) split_tf32(x4[e], hi[e], lo[e]);
+          *reinterpret_cast<float4*>(a_hi + abase + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(a_lo + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready);
+
+      // -- epilogue: bias, GELU, 128 -> V product on this thread's pixel and column half
+      mbar_wait(d_full, (unsigned)it & 1u);
+      tc_fence_after();
+      float o[TC_VP] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        const int j0 = half * 64 + blk * 32;
+        tmem_ld32(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)j0, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float gl = gelu_fast(v[i] + b1s[j0 + i]);
+          const float4 w = *reinterpret_cast<const float4*>(W2s + (j0 + i) * TC_VP);
+          o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
+          o[2] = fmaf(w.z, gl, o[2]); o[3] = fmaf(w.w, gl, o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_free);          // TMEM tile may be overwritten by the next tile's MMAs
+      if (half == 1) *reinterpret_cast<float4*>(ox + m * TC_VP) = make_float4(o[0], o[1], o[2], o[3]);
+      named_bar_sync(1, TC_EPI_WARPS * 32);
+      if (half == 0) {
+        const float4 u = *reinterpret_cast<const float4*>(ox + m * TC_VP);
+        o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
+        const long p = p0 + m;
+        if (p < g.npix) {
+          const float* __restrict__ mean = stats + (size_t)b * 2 * V;
+          const float* __restrict__ sd = mean + V;
+          float* __restrict__ op = out + ((size_t)b * g.npix + p) * V;
+#pragma unroll
+          for (int v = 0; v < TC_VP; ++v)
+            if (v < V) op[v] = fmaf(o[v] + __ldg(b2 + v), __ldg(sd + v), __ldg(mean + v));
+        }
+      }
+      named_bar_sync(1, TC_EPI_WARPS * 32);        // ox is rewritten by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace
+}  // namespace fno
+
+using namespace fno;
+
+extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1, const float* W2, const float* b2,
+                               const float* stats, float* out, int B, int R_in, int W_in, int R_out, int Wp, int C,
+                               int HID, int V, fno_stream_t stream) {
+  if (!h || !W1 || !b1 || !W2 || !b2 || !stats || !out || B <= 0 || R_in <= 0 || W_in <= 0 || R_out < R_in || Wp < W_in) {
+    set_error("fno_head_fwd_tc: bad argument");
+    return FNO_E_ARG;
+  }
+  if (HID != TC_HID || C > TC_KP || C < 1 || V < 1 || V > TC_VP) {
+    set_error("fno_head_fwd_tc: supports hidden width 128, C <= %d, V <= %d (got %d, %d, %d)", TC_KP, TC_VP, HID, C, V);
+    return FNO_E_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HeadGeo g;
+  g.R_in = R_in; g.W_in = W_in; g.R_out = R_out; g.Wp = Wp;
+  g.npix = (long)R_in * W_in;
+  g.plane = (long)R_out * Wp;
+  const long tps = (g.npix + TC_M - 1) / TC_M;
+  const long total = tps * B;
+  if (total > 0x7fffffffL) { set_error("fno_head_fwd_tc: too many tiles"); return FNO_E_ARG; }
+  const size_t smem = 2 * A_BYTES + 2 * B_BYTES + sizeof(float) * (TC_HID * TC_VP + TC_HID + TC_M * TC_VP) +
+                      3 * sizeof(unsigned long long) + 16;
+  static std::atomic<int> done{0};
+  if (!done.load()) {
+    if (cudaFuncSetAttribute(head_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(head_fwd_tc)");
+    done.store(1);
+  }
+  const int ctas = (int)(total < 148 ? total : 148);
+  head_fwd_tc_kernel<<<ctas, TC_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total);
+  count_launch();
+  return check_launch("head_fwd_tc_kernel");
+}

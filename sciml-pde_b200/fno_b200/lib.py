@@ -69,6 +69,7 @@ def load():
             "fno_lift_bwd_workspace_bytes": (C.c_size_t, [i, i, i, i]),
             "fno_lift_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
             "fno_head_fwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
+            "fno_head_fwd_tc": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
             "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
             "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
             "fno_nrmse_workspace_bytes": (C.c_size_t, [i, i]),
@@ -93,7 +94,7 @@ EXPORTED_SYMBOLS = (
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
-    "fno_lift_bwd", "fno_head_fwd", "fno_head_bwd_workspace_bytes", "fno_head_bwd",
+    "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
 )
@@ -341,6 +342,11 @@ def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bia
 # ---------------------------------------------------------------------------------------------
 # lift / projection head (trunk layout h[B, C, R_out, Wp], see include/fno_sm100.h)
 # ---------------------------------------------------------------------------------------------
+import os as _os
+
+HEAD_TC = _os.environ.get("FNO_HEAD_TC", "1") != "0"
+
+
 class TrunkGeo:
     """Geometry of the channel-first padded trunk activation for inputs [B, *spatial, ...]."""
 
@@ -409,6 +415,12 @@ def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
     if tuple(h.shape[2:]) != geo.padded or W1.shape[1] != C or W2.shape[1] != HID:
         raise FnoError(f"head: inconsistent shapes h {tuple(h.shape)}, fc1 {tuple(W1.shape)}, fc2 {tuple(W2.shape)}")
     out = torch.empty((B,) + geo.spatial + (V,), dtype=torch.float32, device=h.device)
+    if HEAD_TC and HID == 128 and C <= 32 and V <= 4:
+        # tensor-core path (tcgen05 kind::tf32, 3xTF32 split: fp32-mode accuracy)
+        _check(load().fno_head_fwd_tc(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                      stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
+               "fno_head_fwd_tc")
+        return out
     _check(load().fno_head_fwd(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()), "fno_head_fwd")
     return out
