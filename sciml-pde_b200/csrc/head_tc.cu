@@ -28,8 +28,6 @@ namespace {
 constexpr int TC_M = 128;          // pixels per tile = TMEM lanes
 constexpr int TC_HID = 128;        // hidden units = accumulator columns
 constexpr int TC_KP = 32;          // channel padding of the staged operands (4 core-matrix groups of 8)
-constexpr int TC_EPI_WARPS = 8;    // loader / epilogue warps: 4 lane quadrants x 2 column halves
-constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1);   // + 1 MMA-issue warp
 constexpr int TC_VP = 4;
 
 struct HeadGeo {
@@ -111,124 +109,161 @@ constexpr int B_BYTES = 16 * 1024;    // [16 hidden groups][8 channel chunks][8]
 
 // ------------------------------------------------------------------------------------------
 // forward:  out = (W2 gelu(W1 h + b1) + b2) * std + mean
+//
+// Persistent CTA, one per SM; 16 loader / epilogue warps (4 TMEM lane quadrants x 4 column quarters)
+// + 1 MMA-issue warp.  Two-stage pipeline over 128-pixel tiles: the operand buffers and the TMEM
+// accumulator are double-buffered, so the MMAs of tile i+1 run while the CUDA cores do the
+// epilogue of tile i, and the global loads of tile i+2 are in flight during that epilogue too.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1)
+constexpr int TCF_EPI_WARPS = 16;
+constexpr int TCF_EPI_THREADS = 32 * TCF_EPI_WARPS;
+constexpr int TCF_THREADS = TCF_EPI_THREADS + 32;
+constexpr int TCF_MAXCH = 2;               // 16-byte channel chunks staged per thread (K <= 32 channels)
+
+__global__ void __launch_bounds__(TCF_THREADS, 1)
 head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
                    const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
                    float* __restrict__ out, HeadGeo g, int C, int V, int tiles_per_sample, int total_tiles) {
   extern __shared__ __align__(128) unsigned char tsm[];
-  unsigned char* a_hi = tsm;                       // A_BYTES
-  unsigned char* a_lo = a_hi + A_BYTES;
-  unsigned char* w_hi = a_lo + A_BYTES;            // B_BYTES
+  unsigned char* a_hi = tsm;                       // [2 stages][A_BYTES]
+  unsigned char* a_lo = a_hi + 2 * A_BYTES;
+  unsigned char* w_hi = a_lo + 2 * A_BYTES;        // B_BYTES
   unsigned char* w_lo = w_hi + B_BYTES;
   float* W2s = reinterpret_cast<float*>(w_lo + B_BYTES);   // [HID][VP]
   float* b1s = W2s + TC_HID * TC_VP;                       // [HID]
-  float* ox = b1s + TC_HID;                                // [TC_M][VP] partial outputs of the upper column half
-  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ox + TC_M * TC_VP);   // a_ready, d_full, d_free
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 3);
+  float* ox = b1s + TC_HID;                                // [2 tiles][4 quarters][TC_M][VP] partial outputs
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ox + 2 * 4 * TC_M * TC_VP);
+  unsigned long long* a_ready = bars;              // [2]
+  unsigned long long* d_full = bars + 2;           // [2]
+  unsigned long long* d_free = bars + 4;           // [2]
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  unsigned long long* a_ready = bars;
-  unsigned long long* d_full = bars + 1;
-  unsigned long long* d_free = bars + 2;
   if (tid == 0) {
-    mbar_init(a_ready, TC_EPI_WARPS);
-    mbar_init(d_full, 1);
-    mbar_init(d_free, TC_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_ready + s, TCF_EPI_WARPS);
+      mbar_init(d_full + s, 1);
+      mbar_init(d_free + s, TCF_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == TC_EPI_WARPS) tmem_alloc(tmem_slot, 128);
+  if (warp == TCF_EPI_WARPS) tmem_alloc(tmem_slot, 256);
   // stage W1 (hi / lo, K-major B operand, zero padded to TC_KP channels), W2^T, b1
-  for (int i = tid; i < TC_HID * TC_KP; i += TC_THREADS) {
+  for (int i = tid; i < TC_HID * TC_KP; i += TCF_THREADS) {
     const int n = i / TC_KP, k = i - n * TC_KP;
     float hi = 0.f, lo = 0.f;
     if (k < C) split_tf32(__ldg(W1 + (size_t)n * C + k), hi, lo);
     *reinterpret_cast<float*>(w_hi + b_off_bytes(n, k)) = hi;
     *reinterpret_cast<float*>(w_lo + b_off_bytes(n, k)) = lo;
   }
-  for (int i = tid; i < TC_HID * TC_VP; i += TC_THREADS) {
+  for (int i = tid; i < TC_HID * TC_VP; i += TCF_THREADS) {
     const int j = i / TC_VP, v = i - j * TC_VP;
     W2s[i] = (v < V) ? __ldg(W2 + (size_t)v * TC_HID + j) : 0.f;
   }
-  for (int i = tid; i < TC_HID; i += TC_THREADS) b1s[i] = __ldg(b1 + i);
-  // zero the A buffers once: channel rows >= C are never written again
-  for (int i = tid; i < 2 * A_BYTES / 16; i += TC_THREADS) reinterpret_cast<float4*>(a_hi)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < TC_HID; i += TCF_THREADS) b1s[i] = __ldg(b1 + i);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
   const int ksteps = (C + 7) / 8;
+  const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
-  if (warp == TC_EPI_WARPS) {
+  if (warp == TCF_EPI_WARPS) {
     // ---- MMA issuer -------------------------------------------------------------------------------
     constexpr unsigned idesc = umma_idesc_tf32(TC_M, TC_HID, /*A K-major*/ 0, /*B K-major*/ 0);
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      mbar_wait(a_ready, (unsigned)it & 1u);
-      mbar_wait(d_free, ((unsigned)it & 1u) ^ 1u);
+    for (int it = 0; it < ntl; ++it) {
+      const int st = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      mbar_wait(a_ready + st, ph);
+      mbar_wait(d_free + st, ph ^ 1u);
       tc_fence_after();
       if (lane == 0) {
         unsigned acc = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi
-          const unsigned char* A = (pass == 0) ? a_lo : a_hi;
+          const unsigned char* A = ((pass == 0) ? a_lo : a_hi) + st * A_BYTES;
           const unsigned char* Bm = (pass == 1) ? w_lo : w_hi;
           for (int ks = 0; ks < ksteps; ++ks) {
             // K = 8 per instruction = two 16-byte chunks: +256 B per K step for both operands
-            tc_mma_tf32(tmem_base, umma_desc(A + ks * 256, 128, 1024), umma_desc(Bm + ks * 256, 128, 1024), idesc, acc);
+            tc_mma_tf32(tmem_base + (unsigned)st * TC_HID, umma_desc(A + ks * 256, 128, 1024),
+                        umma_desc(Bm + ks * 256, 128, 1024), idesc, acc);
             acc = 1;
           }
         }
-        tc_commit(d_full);
+        tc_commit(d_full + st);
       }
       __syncwarp();
     }
   } else {
     // ---- loader / epilogue warps ------------------------------------------------------------------
     const int quad = warp & 3;                     // TMEM lane quadrant of this warp
-    const int half = warp >> 2;                    // column half: hidden units [64 * half, 64 * half + 64)
+    const int colq = warp >> 2;                    // hidden units [32 * colq, 32 * colq + 32)
     const int m = quad * 32 + lane;                // pixel of the tile owned in the epilogue
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / tiles_per_sample;
-      const long p0 = (long)(tile - b * tiles_per_sample) * TC_M;
-      // -- stage the activation tile: thread = (pixel, chunk parity); 4 channels per 16-byte chunk
-      if (it > 0) mbar_wait(d_full, (unsigned)(it - 1) & 1u);   // previous tile's MMAs have consumed A
-      {
-        const int pm = tid & (TC_M - 1);           // pixel of the tile staged by this thread
-        const long p = p0 + pm;
-        const bool valid = p < g.npix;
-        const long r = valid ? p / g.W_in : 0;
-        const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
-        const int abase = (pm & 7) * 16 + (pm >> 3) * 1024;
-        for (int kc = tid >> 7; kc < 2 * ksteps; kc += 2) {
-          float x4[4];
+    const int pm = tid & (TC_M - 1);               // pixel of the tile staged by this thread
+    const int kq = tid >> 7;                       // chunk residue staged by this thread
+    const int abase = (pm & 7) * 16 + (pm >> 3) * 1024;
+    float raw[TCF_MAXCH][4];
+    auto load_raw = [&](int it) {                  // this thread's channels of tile `it` (zeros past the end)
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool in = it < ntl;
+      const int b = in ? tile / tiles_per_sample : 0;
+      const long p = in ? (long)(tile - b * tiles_per_sample) * TC_M + pm : 0;
+      const bool valid = in && p < g.npix;
+      const long r = valid ? p / g.W_in : 0;
+      const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 4 * kc + e;
-            x4[e] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
-          }
+      for (int u = 0; u < TCF_MAXCH; ++u) {
+        const int kc = kq + 4 * u;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = 4 * kc + e;
+          raw[u][e] = (valid && kc < 2 * ksteps && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+        }
+      }
+    };
+    auto store_raw = [&](int st) {
+#pragma unroll
+      for (int u = 0; u < TCF_MAXCH; ++u) {
+        const int kc = kq + 4 * u;
+        if (kc < 2 * ksteps) {
           float hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(x4[e], hi[e], lo[e]);
-          *reinterpret_cast<float4*>(a_hi + abase + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(a_lo + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          for (int e = 0; e < 4; ++e) split_tf32(raw[u][e], hi[e], lo[e]);
+          *reinterpret_cast<float4*>(a_hi + st * A_BYTES + abase + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(a_lo + st * A_BYTES + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready);
+      if (lane == 0) mbar_arrive(a_ready + st);
+    };
+    // prologue: tile 0 staged, tile 1 in flight
+    load_raw(0);
+    store_raw(0);
+    load_raw(1);
+    for (int it = 0; it < ntl; ++it) {
+      const int st = it & 1;
+      const unsigned ph = (unsigned)(it >> 1) & 1u;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = tile / tiles_per_sample;
+      const long p0 = (long)(tile - b * tiles_per_sample) * TC_M;
+      // stage tile it+1 (its operand buffer was last read by the MMAs of tile it-1, whose completion
+      // the previous epilogue observed), then put tile it+2's loads in flight
+      if (it + 1 < ntl) store_raw(st ^ 1);
+      load_raw(it + 2);
 
-      // -- epilogue: bias, GELU, 128 -> V product on this thread's pixel and column half
-      mbar_wait(d_full, (unsigned)it & 1u);
+      // -- epilogue of tile it: bias, GELU, 128 -> V product on this thread's pixel and column quarter
+      mbar_wait(d_full + st, ph);
       tc_fence_after();
       float o[TC_VP] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
+      {
         float v[32];
-        const int j0 = half * 64 + blk * 32;
-        tmem_ld32(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)j0, v);
+        const int j0 = colq * 32;
+        tmem_ld32(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(st * TC_HID + j0), v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_free + st);   // the accumulator may be overwritten by tile it+2's MMAs
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float gl = gelu_fast(v[i] + b1s[j0 + i]);
@@ -237,14 +272,19 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
           o[2] = fmaf(w.z, gl, o[2]); o[3] = fmaf(w.w, gl, o[3]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_free);          // TMEM tile may be overwritten by the next tile's MMAs
-      if (half == 1) *reinterpret_cast<float4*>(ox + m * TC_VP) = make_float4(o[0], o[1], o[2], o[3]);
-      named_bar_sync(1, TC_EPI_WARPS * 32);
-      if (half == 0) {
-        const float4 u = *reinterpret_cast<const float4*>(ox + m * TC_VP);
-        o[0] += u.x; o[1] += u.y; o[2] += u.z; o[3] += u.w;
+      // combine the four column quarters through shared memory (double-buffered: one barrier per
+      // tile); the quarter that finishes the tile rotates so the extra work is spread over all warps
+      float* oxb = ox + (size_t)(it & 1) * 4 * TC_M * TC_VP;
+      *reinterpret_cast<float4*>(oxb + (colq * TC_M + m) * TC_VP) = make_float4(o[0], o[1], o[2], o[3]);
+      named_bar_sync(1, TCF_EPI_THREADS);
+      if (colq == (it & 3)) {
+        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 u = *reinterpret_cast<const float4*>(oxb + (q * TC_M + m) * TC_VP);
+          acc4.x += u.x; acc4.y += u.y; acc4.z += u.z; acc4.w += u.w;
+        }
+        const float of[TC_VP] = {acc4.x, acc4.y, acc4.z, acc4.w};
         const long p = p0 + m;
         if (p < g.npix) {
           const float* __restrict__ mean = stats + (size_t)b * 2 * V;
@@ -252,15 +292,14 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
           float* __restrict__ op = out + ((size_t)b * g.npix + p) * V;
 #pragma unroll
           for (int v = 0; v < TC_VP; ++v)
-            if (v < V) op[v] = fmaf(o[v] + __ldg(b2 + v), __ldg(sd + v), __ldg(mean + v));
+            if (v < V) op[v] = fmaf(of[v] + __ldg(b2 + v), __ldg(sd + v), __ldg(mean + v));
         }
       }
-      named_bar_sync(1, TC_EPI_WARPS * 32);        // ox is rewritten by the next tile
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == TC_EPI_WARPS) tmem_dealloc(tmem_base, 128);
+  if (warp == TCF_EPI_WARPS) tmem_dealloc(tmem_base, 256);
 }
 
 }  // namespace
@@ -287,8 +326,8 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
   const long tps = (g.npix + TC_M - 1) / TC_M;
   const long total = tps * B;
   if (total > 0x7fffffffL) { set_error("fno_head_fwd_tc: too many tiles"); return FNO_E_ARG; }
-  const size_t smem = 2 * A_BYTES + 2 * B_BYTES + sizeof(float) * (TC_HID * TC_VP + TC_HID + TC_M * TC_VP) +
-                      3 * sizeof(unsigned long long) + 16;
+  const size_t smem = 4 * A_BYTES + 2 * B_BYTES + sizeof(float) * (TC_HID * TC_VP + TC_HID + 8 * TC_M * TC_VP) +
+                      6 * sizeof(unsigned long long) + 16;
   static std::atomic<int> done{0};
   if (!done.load()) {
     if (cudaFuncSetAttribute(head_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -296,7 +335,7 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
     done.store(1);
   }
   const int ctas = (int)(total < 148 ? total : 148);
-  head_fwd_tc_kernel<<<ctas, TC_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total);
+  head_fwd_tc_kernel<<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total);
   count_launch();
   return check_launch("head_fwd_tc_kernel");
 }
