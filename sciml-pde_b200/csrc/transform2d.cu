@@ -791,6 +791,7 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
+constexpr size_t kMaxOptinSmemC = 227 * 1024;
 size_t fwd_smem_bytes(const Plan* p, int G) {
   const int NJ = 2 * p->M1T + 1;
   return sizeof(float) * ((size_t)p->NP * p->JP + 2ul * p->m2 * p->WP + (size_t)G * NJ * p->WP);
@@ -814,6 +815,14 @@ int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_o
       return check_launch("cudaFuncSetAttribute(fwd2d)");
     return FNO_OK;
   }
+  if (MINB == 3) {   // experimental class: opt in to large dynamic shared memory on first use
+    static std::atomic<int> done3{0};
+    if (!done3.load()) {
+      cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
+      cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
+      done3.store(1);
+    }
+  }
   const int G = G_launch;
   const unsigned grid = (unsigned)((planes + G - 1) / G);
   if (preact != nullptr)
@@ -836,6 +845,13 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
       return check_launch("cudaFuncSetAttribute(inv2d)");
     return FNO_OK;
   }
+  if (MINB == 3) {
+    static std::atomic<int> done3{0};
+    if (!done3.load()) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
+      done3.store(1);
+    }
+  }
   const int G = G_launch;
   const unsigned grid = (unsigned)((planes + G - 1) / G);
   k<<<grid, threads, smem, st>>>(reinterpret_cast<const float2*>(Y), addend, s_out, out, p->twH, p->twW, p->H,
@@ -847,6 +863,11 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
 inline int round_threads(int n) { return (n + 31) & ~31; }
 constexpr size_t kMaxOptinSmem = 227 * 1024;  // sm_100: 232448 B opt-in per CTA
 constexpr int kSMs = 148;
+// 80-register builds for 3 resident CTAs of <= 224 threads.  Measured at cfg 1 / batch 128: the inverse
+// transform gains (115 -> 101 us, 141 -> 136 us with GELU), the forward transform loses to spills
+// (101 -> 105 us, 174 -> 212 us with GELU'), so only K3 uses it (FNO_T3=1 forces it for K1 as well).
+static const bool kThreeCtasFwd = [] { const char* e = std::getenv("FNO_T3"); return e != nullptr && e[0] == '1'; }();
+static const bool kThreeCtasInv = [] { const char* e = std::getenv("FNO_T3"); return e == nullptr || e[0] != '0'; }();
 
 // Planes per CTA for this launch.  The plan's G maximises lane efficiency; with `planes` known the
 // choice also has to avoid a nearly empty last wave: a launch of n CTAs on 148 * cps resident slots
@@ -886,6 +907,8 @@ int dispatch_fwd_tn(const Plan* p, const float* x, const float* preact, float* d
   // attr_only: opt every instantiation this plan can reach into the device maximum once; the
   // limit is per kernel function, so it must never be lowered by a later, smaller plan
   const size_t smem = attr_only ? kMaxOptinSmem : fwd_smem_bytes(p, G);
+  if (threads <= 224 && !attr_only && kThreeCtasFwd)
+    return launch_fwd_t<M1T, TN, 256, 3>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only, G);
   if (threads <= 288)
     return launch_fwd_t<M1T, TN, 288, 2>(p, x, preact, ds_out, X, planes, cmode, scale, st, threads, smem, attr_only, G);
   if (threads <= 448)
@@ -900,6 +923,8 @@ int dispatch_inv_tn(const Plan* p, const float* Y, const float* addend, float* s
   const int G = attr_only ? p->G_inv : pick_planes_per_cta(p, planes, false, tpp, p->G_inv);
   const int threads = round_threads(G * tpp);
   const size_t smem = attr_only ? kMaxOptinSmem : inv_smem_bytes(p, G);
+  if (threads <= 224 && !attr_only && kThreeCtasInv)
+    return launch_inv_t<M1T, TN, 256, 3>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only, G);
   if (threads <= 288)
     return launch_inv_t<M1T, TN, 288, 2>(p, Y, addend, s_out, out, planes, cmode, scale, apply_gelu, st, threads, smem, attr_only, G);
   if (threads <= 448)
