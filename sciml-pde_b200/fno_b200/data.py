@@ -13,6 +13,7 @@ from __future__ import annotations
 import math
 
 import torch
+import torch.utils.data
 
 
 def cell_centre_grid(n: int, lo: float = -1.0, hi: float = 1.0, nd: int = 2) -> torch.Tensor:
@@ -63,3 +64,27 @@ def synthetic_batch(batch: int, n: int = 128, initial_step: int = 10, channels: 
     xx, yy = windows(traj, initial_step)
     grid = cell_centre_grid(n, nd=nd).unsqueeze(0).expand(batch, *([-1] * (nd + 1))).contiguous()
     return xx, yy, grid
+
+
+class SyntheticWindows(torch.utils.data.Dataset):
+    """Map-style dataset with the sample layout of the reference loaders (fno/utils_2d_rd_baseline.py:
+    59-102): item i -> (xx [X, Y, initial_step, v], yy [X, Y, rollout, v], grid [X, Y, 2]), sliding
+    windows over synthetic diffusion trajectories.  Deterministic in (seed, sizes); used by the
+    loop-level parity fixtures (oracle/make_golden_loop.py, tests/test_loop_parity*.py)."""
+
+    def __init__(self, n_traj: int, n: int, windows: int, initial_step: int = 10, channels: int = 2, seed: int = 0,
+                 rollout: int = 1):
+        steps = initial_step + rollout + windows - 1
+        traj = diffusion_trajectories(n_traj, n, steps, channels, seed)
+        self.xx, self.yy = windows_of(traj, initial_step, rollout)
+        self.grid = cell_centre_grid(n)
+
+    def __len__(self):
+        return self.xx.shape[0]
+
+    def __getitem__(self, i):
+        return self.xx[i], self.yy[i], self.grid
+
+
+def windows_of(traj, initial_step, rollout=1):
+    return windows(traj, initial_step, rollout)
