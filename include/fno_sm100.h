@@ -69,6 +69,14 @@ size_t fno_plan_workspace_bytes(const fno_plan* plan, long planes);
 int fno_sc2d_fwd_transform(const fno_plan* plan, const float* x, const float* preact,
                            float* ds_out, float* X, long planes, int cmode, float scale,
                            fno_stream_t stream);
+/* Same contract with caller-provided scratch (fno_sc2d_fwd_workspace_bytes(plan, planes) bytes; 0 means
+ * the plan has no use for it): lets the library run the contiguous-axis half as a truncated-DFT GEMM
+ * on the tensor cores (tcgen05 kind::tf32, 3xTF32 split) and the strided-axis half on the reduced
+ * [H, 2*m2] data.  With work = NULL it is identical to fno_sc2d_fwd_transform.                     */
+size_t fno_sc2d_fwd_workspace_bytes(const fno_plan* plan, long planes);
+int fno_sc2d_fwd_transform_ws(const fno_plan* plan, const float* x, const float* preact,
+                              float* ds_out, float* X, void* work, long planes, int cmode,
+                              float scale, fno_stream_t stream);
 /* 3-D twin (torch.fft.rfftn, fno/fno.py:262): x [planes, D1, D2, D3] -> X [planes, 2m1, 2m2, m3];
  * work: fno_plan_workspace_bytes(plan, planes) bytes of scratch.                               */
 int fno_sc3d_fwd_transform(const fno_plan* plan, const float* x, const float* preact,

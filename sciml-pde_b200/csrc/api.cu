@@ -96,6 +96,41 @@ int build_plane_tables(Plan* p) {
   return upload(&p->twW, tw);
 }
 
+// hi = rna_tf32(x) (round to nearest, ties away: what cvt.rna.tf32.f32 does), lo = x - hi
+void split_tf32_host(float x, float& hi, float& lo) {
+  unsigned u;
+  std::memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  std::memcpy(&hi, &u, 4);
+  lo = x - hi;
+}
+
+// F[q][w] for the tensor-core W-axis stage: q < m2 cos, m2 <= q < 2*m2 sin, in the K-major UMMA B layout
+//   (q % 8) * 16 + (q / 8) * (nch * 128) + (w / 4) * 128 + (w % 4) * 4  bytes, 32 rows, nch chunks
+int build_tc_tables(Plan* p) {
+  p->tcF_hi = p->tcF_lo = nullptr;
+  p->tc_nch = 0;
+  const int W = p->W, m2 = p->m2;
+  const int KP = (W + 7) & ~7;
+  const int nch = KP / 4;
+  if ((W & 1) || 2 * m2 > 32 || nch > 34) return FNO_OK;   // not eligible: FP32 path only
+  if (fwd2d_tc_smem_bytes(nch) > 227 * 1024) return FNO_OK;
+  std::vector<float> hi((size_t)4 * nch * 32, 0.0f), lo((size_t)4 * nch * 32, 0.0f);
+  for (int q = 0; q < 2 * m2; ++q)
+    for (int w = 0; w < W; ++w) {
+      const int k2 = q < m2 ? q : q - m2;
+      const float v = (float)(q < m2 ? cos2pi((long)k2 * w, W) : sin2pi((long)k2 * w, W));
+      const size_t off = ((size_t)(q & 7) * 16 + (size_t)(q >> 3) * nch * 128 + (size_t)(w >> 2) * 128 + (w & 3) * 4) / 4;
+      split_tf32_host(v, hi[off], lo[off]);
+    }
+  int rc = upload(&p->tcF_hi, hi);
+  if (rc != FNO_OK) return rc;
+  rc = upload(&p->tcF_lo, lo);
+  if (rc != FNO_OK) return rc;
+  p->tc_nch = nch;
+  return launch_fwd2d_tc(p, nullptr, nullptr, nullptr, nullptr, 0, nullptr, true);
+}
+
 void free_plan(Plan* p) {
   if (p == nullptr) return;
   int cur = 0;
@@ -104,6 +139,8 @@ void free_plan(Plan* p) {
   if (p->twH) cudaFree(p->twH);
   if (p->twW) cudaFree(p->twW);
   if (p->twX) cudaFree(p->twX);
+  if (p->tcF_hi) cudaFree(p->tcF_hi);
+  if (p->tcF_lo) cudaFree(p->tcF_lo);
   cudaSetDevice(cur);
   cudaGetLastError();
   delete p;
@@ -150,6 +187,7 @@ int create_common(int device, int nd, int D1, int H, int W, int m1x, int m1, int
     }
   }
   if (rc == FNO_OK) rc = setup_transform2d_attrs(p);
+  if (rc == FNO_OK) rc = build_tc_tables(p);
   cudaSetDevice(cur);
   if (rc != FNO_OK) { free_plan(p); return rc; }
   {
@@ -213,6 +251,20 @@ int fno_sc2d_fwd_transform(const fno_plan* plan, const float* x, const float* pr
   const Plan* p = P(plan);
   if (!p || p->nd != 2 || !x || !X || planes <= 0) { set_error("fno_sc2d_fwd_transform: bad argument"); return FNO_E_ARG; }
   return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, static_cast<cudaStream_t>(stream));
+}
+
+size_t fno_sc2d_fwd_workspace_bytes(const fno_plan* plan, long planes) {
+  const Plan* p = P(plan);
+  if (p == nullptr || p->tc_nch == 0 || planes <= 0) return 0;
+  return sizeof(float) * (size_t)planes * p->H * ((2 * p->m2 + 3) & ~3);
+}
+
+int fno_sc2d_fwd_transform_ws(const fno_plan* plan, const float* x, const float* preact, float* ds_out, float* X,
+                              void* work, long planes, int cmode, float scale, fno_stream_t stream) {
+  const Plan* p = P(plan);
+  if (!p || p->nd != 2 || !x || !X || planes <= 0) { set_error("fno_sc2d_fwd_transform_ws: bad argument"); return FNO_E_ARG; }
+  return launch_fwd2d_ws(p, x, preact, ds_out, X, static_cast<float*>(work), planes, cmode, scale,
+                         static_cast<cudaStream_t>(stream));
 }
 
 int fno_sc2d_inv_transform(const fno_plan* plan, const float* Y, const float* addend, float* s_out, float* out,

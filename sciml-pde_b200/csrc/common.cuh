@@ -30,6 +30,11 @@ struct Plan {
   float* twW;
   float* twX;
   int G_fwd, G_inv;  // planes per CTA
+  // tensor-core W-axis stage of K1 (transform2d_tc.cu): F = [cos | sin](2 pi q w / W) hi / lo in the K-major
+  // UMMA layout, tc_nch 16-byte w chunks per row (0 = path not available for this geometry)
+  float* tcF_hi;
+  float* tcF_lo;
+  int tc_nch;
 };
 
 void set_error(const char* fmt, ...);
@@ -43,6 +48,11 @@ int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_o
 int launch_inv2d(const Plan* p, const float* Y, const float* addend, float* s_out, float* out,
                  long planes, int cmode, float scale, int apply_gelu, cudaStream_t st);
 int setup_transform2d_attrs(const Plan* p);
+int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, float* work,
+                    long planes, int cmode, float scale, cudaStream_t st);
+size_t fwd2d_tc_smem_bytes(int nch);
+int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
+                    cudaStream_t st, bool attr_only);
 int launch_axis_fwd(const Plan* p, const float* S, float* X, long planes, long Q, cudaStream_t st);
 int launch_axis_inv(const Plan* p, const float* Y, float* Z, long planes, long Q, cudaStream_t st);
 int launch_mix_fwd(const Plan* p, const float* X, const float* const* w, float* Y, int B, int Ci,

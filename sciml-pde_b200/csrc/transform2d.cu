@@ -350,6 +350,84 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
 }
 
 // ------------------------------------------------------------------------------------------
+// K1, strided-axis half after the tensor-core W-axis stage (transform2d_tc.cu): per plane the
+// [H, 2*m2] matrix T1 = [sum_w x cos | sum_w x sin] is folded along H exactly like stage 1 of the
+// direct kernel -- thread = (plane, k2) owns the cosine and the sine column of its wavenumber, so
+// the signed-frequency outputs need no exchange between threads:
+//   T1[h] = Tc - i Ts;  with A^c_j = sum_h Tc cos(j th), B^c_j = sum_h Tc sin(j th) (same for Ts)
+//   X[+j, k2] = (A^c - B^s) - i (B^c + A^s),   X[-j, k2] = (A^c + B^s) + i (B^c - A^s)
+// ------------------------------------------------------------------------------------------
+template <int M1T>
+__global__ void __launch_bounds__(256)
+hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float* __restrict__ twH, int H, int W,
+               int m1, int m2, int G, long planes, int cmode, float scale) {
+  constexpr int NJ = Geo<M1T>::NJ;
+  constexpr int JP = Geo<M1T>::JP;
+  const int NP = H / 2 + 1;
+  extern __shared__ __align__(16) float smem[];
+  float* twH_s = smem;                       // [NP][JP]
+  const int tid = threadIdx.x;
+  {
+    const float4* s4 = reinterpret_cast<const float4*>(twH);
+    float4* d4 = reinterpret_cast<float4*>(twH_s);
+    for (int i = tid; i < NP * JP / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+  }
+  __syncthreads();
+  const int g = tid / m2;
+  const int k2 = tid - g * m2;
+  const long plane = (long)blockIdx.x * G + g;
+  if (g >= G || plane >= planes) return;
+  const int TQ = (2 * m2 + 3) & ~3;          // row pitch of T1 (transform2d_tc.cu)
+  const float* __restrict__ tp = T1 + (size_t)plane * H * TQ + k2;
+  auto ld = [&](int h) -> Vec<2> {
+    Vec<2> v;
+    v.v[0] = __ldg(tp + (size_t)h * TQ);
+    v.v[1] = __ldg(tp + (size_t)h * TQ + m2);
+    return v;
+  };
+  float acc[2][NJ];
+#pragma unroll
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc[n][j] = 0.0f;
+  fold_accumulate_even<M1T, 2>(acc, twH_s, ld(0));
+  const int npairs = (H - 1) / 2;
+  constexpr int PG = 4;
+  int t = 1;
+  for (; t + PG - 1 <= npairs; t += PG) {
+    Vec<2> v1[PG], v2[PG];
+#pragma unroll
+    for (int u = 0; u < PG; ++u) { v1[u] = ld(t + u); v2[u] = ld(H - t - u); }
+#pragma unroll
+    for (int u = 0; u < PG; ++u) {
+      Vec<2> e, o;
+#pragma unroll
+      for (int n = 0; n < 2; ++n) { e.v[n] = v1[u].v[n] + v2[u].v[n]; o.v[n] = v1[u].v[n] - v2[u].v[n]; }
+      fold_accumulate<M1T, 2>(acc, twH_s + (t + u) * JP, e, o);
+    }
+  }
+  for (; t <= npairs; ++t) {
+    const Vec<2> a = ld(t), b = ld(H - t);
+    Vec<2> e, o;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) { e.v[n] = a.v[n] + b.v[n]; o.v[n] = a.v[n] - b.v[n]; }
+    fold_accumulate<M1T, 2>(acc, twH_s + t * JP, e, o);
+  }
+  if ((H & 1) == 0) fold_accumulate_even<M1T, 2>(acc, twH_s + (H / 2) * JP, ld(H / 2));
+  float sc = scale;
+  if (cmode && k2 != 0 && !((W & 1) == 0 && 2 * k2 == W)) sc *= 2.0f;
+  float2* Xp = X + (size_t)plane * (2 * m1) * m2;
+#pragma unroll
+  for (int j = 0; j <= M1T; ++j) {
+    if (j > m1) break;
+    const float Ac = acc[0][j], As = acc[1][j];
+    const float Bc = (j > 0) ? acc[0][M1T + j] : 0.f, Bs = (j > 0) ? acc[1][M1T + j] : 0.f;
+    if (j < m1) Xp[(size_t)j * m2 + k2] = make_float2((Ac - Bs) * sc, -(Bc + As) * sc);
+    if (j >= 1) Xp[(size_t)(2 * m1 - j) * m2 + k2] = make_float2((Ac + Bs) * sc, (Bc - As) * sc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K1, TMA-fed persistent form (planes of <= ~68 KB with 16-byte-multiple size, even W, M1T <= 16)
 //
 // One CTA per SM loops over planes.  A producer warp streams whole planes -- a plane is one
@@ -1028,6 +1106,43 @@ int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_o
   if (preact == nullptr && (reinterpret_cast<size_t>(x) & 15) == 0 && planes >= 2 * kSMs && fwd_tma_eligible(p))
     return dispatch_fwd_tma(p, x, X, planes, cmode, scale, st, false);
   FNO_DISPATCH_M1T(dispatch_fwd, p, x, preact, ds_out, X, planes, cmode, scale, st, false)
+}
+
+template <int M1T>
+static int launch_hpass_t(const Plan* p, const float* T1, float* X, long planes, int cmode, float scale, cudaStream_t st) {
+  int G = 256 / p->m2;
+  if (G > 8) G = 8;                                   // ~100-thread CTAs: enough CTAs to cover 148 SMs
+  const int threads = round_threads(G * p->m2);
+  const size_t smem = sizeof(float) * (size_t)p->NP * p->JP;
+  const unsigned grid = (unsigned)((planes + G - 1) / G);
+  hpass2d_kernel<M1T><<<grid, threads, smem, st>>>(T1, reinterpret_cast<float2*>(X), p->twH, p->H, p->W, p->m1, p->m2, G,
+                                                   planes, cmode, scale);
+  count_launch();
+  return check_launch("hpass2d_kernel");
+}
+
+// K1 with a caller-provided workspace: W-axis stage on the tensor cores + H-axis fold on the FP32 pipes
+// when the geometry allows (even W <= 136, 2*m2 <= 32) and the batch is large enough to fill the
+// persistent grid; otherwise the direct kernel.  The caller opts in by passing the workspace: at
+// width 20 / fp32 mode the direct kernel is faster (137 vs 101 us at cfg 1).
+int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, float* work,
+                    long planes, int cmode, float scale, cudaStream_t st) {
+  const bool aligned = ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(preact) | reinterpret_cast<size_t>(ds_out)) & 7) == 0 &&
+                       (reinterpret_cast<size_t>(work) & 15) == 0;
+  if (work == nullptr || p->tc_nch == 0 || !aligned || planes * p->H < 4096 ||
+      sizeof(float) * (size_t)p->NP * p->JP > 48 * 1024)
+    return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
+  int rc = launch_fwd2d_tc(p, x, preact, ds_out, work, planes, st, false);
+  if (rc != FNO_OK) return rc;
+  switch (p->M1T) {
+    case 4: return launch_hpass_t<4>(p, work, X, planes, cmode, scale, st);
+    case 8: return launch_hpass_t<8>(p, work, X, planes, cmode, scale, st);
+    case 12: return launch_hpass_t<12>(p, work, X, planes, cmode, scale, st);
+    case 16: return launch_hpass_t<16>(p, work, X, planes, cmode, scale, st);
+    case 24: return launch_hpass_t<24>(p, work, X, planes, cmode, scale, st);
+    case 32: return launch_hpass_t<32>(p, work, X, planes, cmode, scale, st);
+    default: set_error("unsupported padded modes1 %d", p->M1T); return FNO_E_ARG;
+  }
 }
 
 int launch_inv2d(const Plan* p, const float* Y, const float* addend, float* s_out, float* out, long planes,

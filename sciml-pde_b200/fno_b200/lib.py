@@ -7,6 +7,7 @@ Python and there is no CPU / eager fallback -- a missing library or a non-CUDA t
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 from typing import Optional, Sequence
@@ -55,6 +56,8 @@ def load():
             "fno_plan_destroy": (i, [vp]),
             "fno_plan_workspace_bytes": (C.c_size_t, [vp, l]),
             "fno_sc2d_fwd_transform": (i, [vp, vp, vp, vp, vp, l, i, f, vp]),
+            "fno_sc2d_fwd_workspace_bytes": (C.c_size_t, [vp, l]),
+            "fno_sc2d_fwd_transform_ws": (i, [vp, vp, vp, vp, vp, vp, l, i, f, vp]),
             "fno_sc3d_fwd_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, vp]),
             "fno_mix_fwd": (i, [vp, vp, vpp, vp, i, i, i, vp]),
             "fno_mix_bwd": (i, [vp, vp, vp, vpp, vp, vpp, i, i, i, vp]),
@@ -87,10 +90,15 @@ def load():
     return _lib
 
 
+# K1 with its contiguous-axis half as a tcgen05 truncated-DFT GEMM (transform2d_tc.cu).  Opt-in: at
+# width 20 in fp32 mode (3xTF32) the direct FP32 kernel is faster.
+K1_TENSOR_CORES = os.environ.get("FNO_K1_TC", "0") == "1"
+
 EXPORTED_SYMBOLS = (
     "fno_version", "fno_sm_arch", "fno_last_error", "fno_launch_count", "fno_shutdown",
     "fno_plan2d_create", "fno_plan3d_create", "fno_plan_destroy", "fno_plan_workspace_bytes",
-    "fno_sc2d_fwd_transform", "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
+    "fno_sc2d_fwd_transform", "fno_sc2d_fwd_workspace_bytes", "fno_sc2d_fwd_transform_ws",
+    "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
@@ -218,8 +226,14 @@ def fwd_transform(plan: Plan, x: torch.Tensor, *, preact: Optional[torch.Tensor]
     X = torch.empty(tuple(x.shape[:-plan.nd]) + plan.spec_shape, dtype=torch.complex64, device=x.device)
     lib = load()
     if plan.nd == 2:
-        rc = lib.fno_sc2d_fwd_transform(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(), planes,
-                                        cmode, scale, _stream())
+        nbytes = lib.fno_sc2d_fwd_workspace_bytes(plan.handle, planes) if K1_TENSOR_CORES else 0
+        if nbytes:
+            work = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+            rc = lib.fno_sc2d_fwd_transform_ws(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(),
+                                               work.data_ptr(), planes, cmode, scale, _stream())
+        else:
+            rc = lib.fno_sc2d_fwd_transform(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(), planes,
+                                            cmode, scale, _stream())
     else:
         work = plan.workspace(planes, x.device)
         rc = lib.fno_sc3d_fwd_transform(plan.handle, x.data_ptr(), _ptr(preact), _ptr(ds_out), X.data_ptr(),

@@ -350,3 +350,45 @@ def test_head_forward_backward(lib, spatial, C, V, B):
     assert float(hc.grad.cpu()[pad_mask].abs().max()) == 0.0
     for t, name in zip(leaves, ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")):
         assert O.rel_err(t.grad.cpu().numpy(), p[name].grad.numpy()) < TOL, name
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core W-axis stage of K1 (transform2d_tc.cu, tcgen05 kind::tf32 with 3xTF32 split) + FP32
+# H-axis fold: opt-in (lib.K1_TENSOR_CORES); taken when planes * H >= 4096 rows, W even and <= 136, 2 * m2 <= 32
+# ---------------------------------------------------------------------------------------------
+TC_PLANES = [
+    # B, C, H, W, m1, m2
+    (4, 20, 130, 130, 12, 12),      # cfg 1 plane; 80 planes = 81.25 row tiles (ragged last tile)
+    (3, 16, 96, 70, 12, 12),        # a 3-D slice width (W = 70: 18 chunks, last chunk half valid)
+    (2, 24, 100, 136, 16, 16),      # widest supported row, 2 * m2 = 32 accumulator columns
+    (5, 9, 129, 66, 5, 7),          # odd H, modes below the padded template sizes
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", TC_PLANES)
+@pytest.mark.parametrize("cmode", [0, 1])
+def test_fwd_transform_tensor_core_path(lib, monkeypatch, B, C, H, W, m1, m2, cmode):
+    monkeypatch.setattr(lib, "K1_TENSOR_CORES", True)
+    rng = np.random.default_rng(H * 7 + W)
+    x = (rng.standard_normal((B, C, H, W)) * 3 + 0.5).astype(np.float32)
+    scale = 1.0 if cmode == 0 else 1.0 / (H * W)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    assert lib.load().fno_sc2d_fwd_workspace_bytes(plan.handle, B * C) == 4 * B * C * H * ((2 * m2 + 3) // 4 * 4)
+    X = lib.fwd_transform(plan, dev(x), cmode=cmode, scale=scale).cpu().numpy()
+    ref = O.fwd_transform(x, (m1, m2), cmode=cmode, scale=scale)
+    assert O.rel_err(X, ref) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", TC_PLANES[:2])
+def test_fwd_transform_tensor_core_path_with_gelu_grad(lib, monkeypatch, B, C, H, W, m1, m2):
+    monkeypatch.setattr(lib, "K1_TENSOR_CORES", True)
+    rng = np.random.default_rng(99)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s = (rng.standard_normal((B, C, H, W)) * 1.5).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    ds = torch.empty(B, C, H, W, device="cuda")
+    X = lib.fwd_transform(plan, dev(g), preact=dev(s), ds_out=ds, cmode=1, scale=1.0 / (H * W)).cpu().numpy()
+    ds_ref = g.astype(np.float64) * O.gelu_grad(s.astype(np.float64))
+    assert O.rel_err(ds.cpu().numpy(), ds_ref) < TOL
+    ref = O.fwd_transform(ds_ref, (m1, m2), cmode=1, scale=1.0 / (H * W))
+    assert O.rel_err(X, ref) < TOL

@@ -29,14 +29,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 __global__ void __launch_bounds__(160, 1) probe(float* D, int variant, int ksteps, int N) {
   extern __shared__ __align__(1024) unsigned char sm[];
   unsigned char* A = sm;                 // 16 KB
-  unsigned char* Bm = sm + 16384;        // 16 KB
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + 32768);
-  unsigned* slot = reinterpret_cast<unsigned*>(sm + 32768 + 16);
+  unsigned char* Bm = sm + 20480;        // 16 KB
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + 36864);
+  unsigned* slot = reinterpret_cast<unsigned*>(sm + 36864 + 16);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool a_kmajor = (variant & 4) != 0 || (variant & 16) != 0;
   const bool a_sw128 = (variant & 8) != 0;
   const bool b_mn = (variant & 16) != 0;
-  for (int i = tid; i < 8192; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
+  for (int i = tid; i < 9216; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 0.f;
   __syncthreads();
   // A[m][k] = one-hot at k == (m % (8*ksteps));  B[n][k] = 8n + k  (k < 8*ksteps)
   const int K = 8 * ksteps;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(160, 1) probe(float* D, int variant, int kstep
     int off;
     if (a_sw128) off = ((((m >> 2) & 7) ^ (k & 7)) * 16) + (m & 3) * 4 + (k & 7) * 128 + (m >> 5) * 1024 + (k >> 3) * 4096;
     else if (!a_kmajor) off = (m & 3) * 4 + (m >> 2) * 128 + (k & 7) * 16 + (k >> 3) * 4096;
+    else if (variant & 64) off = (m & 7) * 16 + (m >> 3) * (8 * 144) + (k >> 2) * 144 + (k & 3) * 4;
     else off = (m & 7) * 16 + (m >> 3) * 1024 + (k >> 2) * 128 + (k & 3) * 4;
     *reinterpret_cast<float*>(A + off) = v;
   }
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(160, 1) probe(float* D, int variant, int kstep
       unsigned a_lbo = 4096, a_sbo = 128, b_lbo = 128, b_sbo = 1024;
       const unsigned char* Ap = A + ks * 4096;
       if (a_kmajor) { a_lbo = 128; a_sbo = 1024; Ap = A + ks * 256; }
+      if (variant & 64) { a_lbo = 144; a_sbo = 8 * 144; Ap = A + ks * 288; }
       unsigned a_layout = 0;
       if (a_sw128) { a_lbo = 1024; a_sbo = 4096; a_layout = 2; }
       if (b_mn) { b_lbo = 4096; b_sbo = 128; }
@@ -115,7 +117,7 @@ int main() {
   cudaMalloc(&D, 128 * 128 * 4);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 40000);
   std::vector<float> h(128 * 128);
-  const int cases[][3] = {{4, 1, 128}, {4, 3, 128}, {4, 3, 32}, {8, 1, 128}, {9, 1, 128}, {8, 3, 128}, {16, 1, 128}, {18, 1, 128}, {16, 3, 32}, {0, 1, 128}};
+  const int cases[][3] = {{68, 1, 32}, {68, 3, 32}, {68, 3, 128},{4, 1, 128}, {4, 3, 128}, {4, 3, 32}, {8, 1, 128}, {9, 1, 128}, {8, 3, 128}, {16, 1, 128}, {18, 1, 128}, {16, 3, 32}, {0, 1, 128}};
   for (auto& c : cases) {
     const int variant = c[0], ks = c[1], N = c[2], K = 8 * ks;
     cudaMemset(D, 0xff, 128 * 128 * 4);
