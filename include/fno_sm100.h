@@ -168,6 +168,13 @@ int fno_head_bwd(const float* h, const float* dout, const float* W1, const float
                  const float* stats, float* dh, float* gW1, float* gb1, float* gW2, float* gb2,
                  void* work, int B, int R_in, int W_in, int R_out, int Wp, int C, int HID, int V,
                  fno_stream_t stream);
+/* Same contract on the tensor cores (head_bwd_tc.cu: the hidden-layer recompute, dh = dpre W1 and
+ * gW1 = dpre^T h as tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM); requires
+ * HID = 128, C <= 23, V <= 4.  Same workspace size.                                                 */
+int fno_head_bwd_tc(const float* h, const float* dout, const float* W1, const float* b1,
+                    const float* W2, const float* stats, float* dh, float* gW1, float* gb1,
+                    float* gW2, float* gb2, void* work, int B, int R_in, int W_in, int R_out, int Wp,
+                    int C, int HID, int V, fno_stream_t stream);
 
 /* ---- step tail: loss, gradient clipping, Adam, LR schedule --------------------- */
 /* nrmse(out, target).mean() of fno/train.py:34-40,:266-267 for out / target [B, P, V] (P = pixels x

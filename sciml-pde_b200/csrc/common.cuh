@@ -53,6 +53,8 @@ int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* d
 size_t fwd2d_tc_smem_bytes(int nch);
 int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
                     cudaStream_t st, bool attr_only);
+size_t head_bwd_tc_workspace_bytes();
+int head_pad_zero(float* dh, int R_in, int W_in, int R_out, int Wp, long planes, cudaStream_t st);
 int launch_axis_fwd(const Plan* p, const float* S, float* X, long planes, long Q, cudaStream_t st);
 int launch_axis_inv(const Plan* p, const float* Y, float* Z, long planes, long Q, cudaStream_t st);
 int launch_mix_fwd(const Plan* p, const float* X, const float* const* w, float* Y, int B, int Ci,
@@ -126,6 +128,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 // bounded wait: a protocol bug traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
   const unsigned addr = smem_u32(bar);
+#pragma unroll 1
   for (unsigned spin = 0; spin < (1u << 28); ++spin) {
     unsigned ok;
     asm volatile(

@@ -720,6 +720,13 @@ int launch_pad_zero(float* h, const PixGeo& g, long planes, cudaStream_t st) {
 }  // namespace
 }  // namespace fno
 
+namespace fno {
+// zero padding of a trunk-layout gradient tensor (used by head_bwd_tc.cu as well)
+int head_pad_zero(float* dh, int R_in, int W_in, int R_out, int Wp, long planes, cudaStream_t st) {
+  return launch_pad_zero(dh, make_geo(R_in, W_in, R_out, Wp), planes, st);
+}
+}  // namespace fno
+
 using namespace fno;
 
 #define FNO_DISPATCH_CPVP(FN, ...)                                                         \
@@ -859,7 +866,9 @@ extern "C" size_t fno_head_bwd_workspace_bytes(int C, int HID, int V) {
   const int CP = pick_cp(C);
   if (CP < 0 || HID < 1 || V < 1 || V > 8) return 0;
   const int VP = V <= 4 ? 4 : 8;
-  return sizeof(float) * (size_t)PERSIST_CTAS * ((size_t)HID * CP + HID + (size_t)VP * HID + VP);
+  const size_t fp32_path = sizeof(float) * (size_t)PERSIST_CTAS * ((size_t)HID * CP + HID + (size_t)VP * HID + VP);
+  const size_t tc_path = head_bwd_tc_workspace_bytes();      // fno_head_bwd_tc shares the workspace contract
+  return fp32_path > tc_path ? fp32_path : tc_path;
 }
 
 extern "C" int fno_head_bwd(const float* h, const float* dout, const float* W1, const float* b1, const float* W2,

@@ -34,6 +34,29 @@ __device__ __forceinline__ void tc_mma_tf32(unsigned d_tmem, unsigned long long 
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Whole-warp forms: the warp stays converged and one elected lane issues.  With `if (lane == 0) mma(...)`
+// the compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY loop and rebuilds the descriptors in the
+// uniform datapath (~16 dependent instructions, ~130 cycles per MMA: the issuing thread becomes the
+// bottleneck for small-N MMAs -- profiles/r1_h); with the election inside the asm ptxas emits
+// back-to-back UTCHMMAs.
+__device__ __forceinline__ void tc_mma_tf32_elect(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                                  unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(unsigned long long* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane of its warp's quadrant)
 __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
   unsigned r[32];
@@ -50,6 +73,56 @@ __device__ __forceinline__ void tmem_ld32(unsigned taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// A operand read from TENSOR MEMORY (row m in lane m, K along 32-bit columns; verified by
+// tools/ubench/umma_tmemA_probe.cu for M = 128), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts_elect(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc,
+                                                     unsigned idesc, unsigned accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 registers -> 32 lanes x 16 consecutive fp32 columns (no wait: pair with tmem_st_wait())
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+        "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+        "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
+        "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 / 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+  unsigned r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor): start >> 4 in bits [0,14),

@@ -75,6 +75,7 @@ def load():
             "fno_head_fwd_tc": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, vp]),
             "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
             "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
+            "fno_head_bwd_tc": (i, [vp] * 12 + [i] * 8 + [vp]),
             "fno_nrmse_workspace_bytes": (C.c_size_t, [i, i]),
             "fno_nrmse_fwd": (i, [vp, vp, vp, vp, i, l, i, vp]),
             "fno_nrmse_bwd": (i, [vp, vp, vp, vp, vp, i, l, i, vp]),
@@ -102,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
-    "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd",
+    "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
 )
@@ -359,6 +360,7 @@ def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bia
 import os as _os
 
 HEAD_TC = _os.environ.get("FNO_HEAD_TC", "1") != "0"
+HEAD_BWD_TC = _os.environ.get("FNO_HEAD_BWD_TC", "1") != "0"
 
 
 class TrunkGeo:
@@ -448,7 +450,10 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
     dh = torch.empty_like(h)
     gW1, gb1 = torch.empty_like(W1), torch.empty(HID, dtype=torch.float32, device=h.device)
     gW2, gb2 = torch.empty_like(W2), torch.empty(V, dtype=torch.float32, device=h.device)
-    _check(lib.fno_head_bwd(h.data_ptr(), dout.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
-                            stats.data_ptr(), dh.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(),
-                            gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()), "fno_head_bwd")
+    tc = HEAD_BWD_TC and HID == 128 and C <= 23 and V <= 4
+    fn = lib.fno_head_bwd_tc if tc else lib.fno_head_bwd      # tcgen05 3xTF32 path / FP32 CUDA-core path
+    _check(fn(h.data_ptr(), dout.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
+              stats.data_ptr(), dh.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(),
+              gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
+           "fno_head_bwd_tc" if tc else "fno_head_bwd")
     return dh, gW1, gb1, gW2, gb2

@@ -308,11 +308,18 @@ HEAD_CASES = [
     ((6, 6, 10), 20, 5, 2),
     ((12, 10), 32, 4, 2),
     ((8, 8), 64, 3, 1),
+    ((64, 64), 20, 2, 5),       # 320 64-pixel tiles: several pipelined tiles per persistent CTA (tensor-core backward)
+    ((40, 50), 23, 4, 3),       # widest tensor-core case (C + bias column = 24), ragged last tile, V = 4
+    ((128, 128), 20, 2, 2),     # cfg-1 plane
 ]
 
 
+@pytest.mark.parametrize("bwd_tc", [True, False], ids=["tcgen05", "fp32"])
 @pytest.mark.parametrize("spatial,C,V,B", HEAD_CASES)
-def test_head_forward_backward(lib, spatial, C, V, B):
+def test_head_forward_backward(lib, monkeypatch, spatial, C, V, B, bwd_tc):
+    monkeypatch.setattr(lib, "HEAD_BWD_TC", bwd_tc)
+    if bwd_tc and (C > 23 or V > 4):
+        pytest.skip("outside the tensor-core backward's envelope (FP32 path covers it)")
     from fno_b200 import ops
     from oracle import fno_port as P
 
