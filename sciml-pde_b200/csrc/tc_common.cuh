@@ -141,10 +141,10 @@ __host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int N, int a_mn_ma
          ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
 }
 
+// hi = rna_tf32(x) (round to nearest, ties away), lo = x - hi (exact).  cvt.rna.tf32.f32 compiles to four
+// instructions (it preserves inf / NaN); the integer form is two and identical for finite values.
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  unsigned h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
   lo = x - hi;
 }
 
