@@ -73,22 +73,6 @@ __device__ long long g_trace[16 * 32];
 #define TRACE(slot) do { } while (0)
 #endif
 
-// exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery): 4 instructions instead
-// of the ~35 of a hardware-less integer division -- a loader warp is one dependent instruction stream
-struct FastDiv {
-  unsigned d, m, l;
-  __host__ void init(unsigned div) {
-    d = div;
-    l = 0;
-    while ((1ull << l) < div) ++l;
-    m = (unsigned)(((1ull << 32) * ((1ull << l) - div)) / div + 1);
-  }
-  __device__ __forceinline__ unsigned div(unsigned n) const {
-    const unsigned t = __umulhi(m, n);
-    return l == 0 ? n : (t + ((n - t) >> 1)) >> (l - 1);
-  }
-};
-
 struct BtGeo {
   int R_in, W_in, R_out, Wp;
   long npix, plane;

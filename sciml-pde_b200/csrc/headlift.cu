@@ -206,12 +206,13 @@ constexpr int LB_CTAS = 148 * 3;
 struct TileMap {
   int tiles_per_row;
   int total;
+  FastDiv by_tpr, by_rows;
 };
 __device__ __forceinline__ void decode_tile(const TileMap& tm, const PixGeo& g, int tile, int& b, int& r, int& w0) {
-  const int wc = tile % tm.tiles_per_row;
-  const int t = tile / tm.tiles_per_row;
-  r = t % g.R_in;
-  b = t / g.R_in;
+  const int t = (int)tm.by_tpr.div((unsigned)tile);
+  const int wc = tile - t * tm.tiles_per_row;
+  b = (int)tm.by_rows.div((unsigned)t);
+  r = t - b * g.R_in;
   w0 = wc * TILE;
 }
 
@@ -300,6 +301,169 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
     for (int q = 0; q < 4; ++q)
       if (4 * fq + q <= F) pp[(size_t)c * (F + 1) + 4 * fq + q] = acc[kk][q];
     if (KSPL == 2) break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// lift backward, register-tiled form (taken when the feature count is a multiple of 4 and the output
+// tile is small): gW0[c, f] = sum_px dh[c, px] feat[px, f].
+// The features are staged PIXEL-major, feat[px][FR], straight from the contiguous channels-last x tile
+// with coalesced 16-byte loads (normalised on the way through registers); the gradient keeps its channel
+// rows.  A thread owning a 4-channel x 4-feature block of the output needs one LDS.128 and four
+// broadcast LDS.32 per pixel for its 16 FMAs (the first form: five LDS.128 per 16, bound by the
+// shared-memory pipe), and the next tile's global data travels in registers under the products.
+// Warp w accumulates pixels 8w..8w+7 of every tile; the eight pixel slices are combined once per CTA.
+// ------------------------------------------------------------------------------------------
+constexpr int LB2_THREADS = 256;
+constexpr int LB2_SLICE = TILE / (LB2_THREADS / 32);    // pixels per warp and tile (8)
+
+template <int NIT>
+__global__ void __launch_bounds__(LB2_THREADS, 3)
+lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, const float* __restrict__ stats,
+                 const float* __restrict__ dh, float* __restrict__ part, PixGeo g, TileMap tm, int T, int V, int G,
+                 int C) {
+  extern __shared__ __align__(16) float sm[];
+  const int F1 = T * V, F = F1 + G;
+  const int FR = (F + 1 + 3) & ~3, FQ = FR / 4;
+  const int CQ = (C + 3) / 4, CR = 4 * CQ;
+  const int nitems = CQ * FQ;
+  float* feat = sm;                           // [TILE][FR]
+  float* dhs = feat + TILE * FR;              // [CR][TP]: channel rows (pad rows zero)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // constant columns: bias feature = 1, padding = 0
+  for (int i = tid; i < TILE * (FR - F); i += LB2_THREADS) {
+    const int px = i / (FR - F), q = i - px * (FR - F);
+    feat[px * FR + F + q] = (q == 0) ? 1.f : 0.f;
+  }
+  for (int i = tid; i < TP * (CR - C); i += LB2_THREADS) dhs[C * TP + i] = 0.f;
+  int cq[NIT], fq[NIT];
+  float acc[NIT][4][4];
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int item = lane + 32 * k;
+    const int it = item < nitems ? item : 0;
+    fq[k] = it / CQ;
+    cq[k] = it - fq[k] * CQ;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[k][a][b] = 0.f;
+  }
+  const int F4 = F1 / 4;
+  // software pipeline: the next tile's global data travels in registers while this tile's products run.
+  // Everything that does not depend on the tile (which element of the tile a thread stages, where it goes in
+  // shared memory, which variable it belongs to) is computed once: run-time integer divisions inside the
+  // tile loop cost more instructions than the products.
+  constexpr int XR = 2;                       // float4 of x per thread and tile (TILE * F4 <= XR * 256)
+  constexpr int DR = 3;                       // float2 of dh per thread and tile (C * TILE / 2 <= DR * 256)
+  float4 xr[XR];
+  float2 dr[DR];
+  float gr;
+  int xpx[XR], xdst[XR], xvi[XR];             // pixel (TILE = not staged), feat offset, variable of element 0
+#pragma unroll
+  for (int u = 0; u < XR; ++u) {
+    const int i = tid + u * LB2_THREADS;
+    const int px = i / F4, q = i - px * F4;
+    xpx[u] = (i < TILE * F4) ? px : TILE;
+    xdst[u] = px * FR + 4 * q;
+    xvi[u] = (4 * q) % V;
+  }
+  const int gpx = (tid < TILE * G) ? tid / G : TILE;
+  const int gdst = (tid < TILE * G) ? gpx * FR + F1 + (tid - gpx * G) : 0;
+  int pb = 0, pnv = 0;
+  auto prefetch = [&](int tile) {
+    int b, r, w0;
+    decode_tile(tm, g, tile, b, r, w0);
+    pb = b;
+    pnv = (g.W_in - w0 < TILE) ? g.W_in - w0 : TILE;
+    const size_t pidx = (size_t)b * g.npix + (size_t)r * g.W_in + w0;
+    const float4* __restrict__ xp = reinterpret_cast<const float4*>(x + pidx * F1);
+#pragma unroll
+    for (int u = 0; u < XR; ++u)
+      xr[u] = (xpx[u] < pnv) ? __ldg(xp + tid + u * LB2_THREADS) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gr = (gpx < pnv) ? __ldg(grid + pidx * G + tid) : 0.f;
+    // channel rows of the gradient: 8-byte coalesced loads (pixel pairs)
+    const float* __restrict__ dp = dh + (size_t)b * C * g.plane + (size_t)r * g.Wp + w0 + 2 * lane;
+#pragma unroll
+    for (int u = 0; u < DR; ++u) {
+      const int c = warp + u * (LB2_THREADS / 32);
+      float2 v = make_float2(0.f, 0.f);
+      if (c < C) {
+        const float* __restrict__ q = dp + (size_t)c * g.plane;
+        if (2 * lane + 1 < pnv) v = __ldg(reinterpret_cast<const float2*>(q));
+        else if (2 * lane < pnv) v.x = __ldg(q);
+      }
+      dr[u] = v;
+    }
+  };
+  if ((int)blockIdx.x < tm.total) prefetch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x) {
+    const float* __restrict__ mean = stats + (size_t)pb * 2 * V;
+    const float* __restrict__ sd = mean + V;
+    __syncthreads();                          // the previous tile's products are done
+#pragma unroll
+    for (int u = 0; u < XR; ++u) {
+      if (xpx[u] < TILE) {
+        float4 v = xr[u];
+        if (xpx[u] < pnv) {
+          int vi = xvi[u];
+          float* e = reinterpret_cast<float*>(&v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            e[k] = (e[k] - __ldg(mean + vi)) * (1.0f / __ldg(sd + vi));
+            if (++vi == V) vi = 0;
+          }
+        }
+        *reinterpret_cast<float4*>(feat + xdst[u]) = v;
+      }
+    }
+    if (gpx < TILE) feat[gdst] = gr;
+#pragma unroll
+    for (int u = 0; u < DR; ++u) {
+      const int c = warp + u * (LB2_THREADS / 32);
+      if (c < C) *reinterpret_cast<float2*>(dhs + c * TP + 2 * lane) = dr[u];
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < tm.total) prefetch(tile + gridDim.x);
+#pragma unroll
+    for (int j = 0; j < LB2_SLICE; ++j) {
+      const int px = warp * LB2_SLICE + j;
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        const float* __restrict__ dq = dhs + 4 * cq[k] * TP + px;
+        const float4 f = *reinterpret_cast<const float4*>(feat + px * FR + 4 * fq[k]);
+        const float dv[4] = {dq[0], dq[TP], dq[2 * TP], dq[3 * TP]}, fv[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int bb = 0; bb < 4; ++bb) acc[k][a][bb] = fmaf(dv[a], fv[bb], acc[k][a][bb]);
+      }
+    }
+  }
+  // combine the eight pixel slices, then one partial record per CTA: part[cta][c][F + 1]
+  __syncthreads();
+  float* red = sm;                            // [8 warps][nitems][16]
+#pragma unroll
+  for (int k = 0; k < NIT; ++k) {
+    const int item = lane + 32 * k;
+    if (item < nitems) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        *reinterpret_cast<float4*>(red + ((size_t)warp * nitems + item) * 16 + 4 * a) =
+            make_float4(acc[k][a][0], acc[k][a][1], acc[k][a][2], acc[k][a][3]);
+    }
+  }
+  __syncthreads();
+  float* __restrict__ pp = part + (size_t)blockIdx.x * C * (F + 1);
+  for (int o = tid; o < nitems * 16; o += LB2_THREADS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < LB2_THREADS / 32; ++w) sum += red[(size_t)w * nitems * 16 + o];
+    const int item = o >> 4, a = (o >> 2) & 3, bb = o & 3;
+    const int f_q = item / CQ, c_q = item - f_q * CQ;
+    const int c = 4 * c_q + a, f = 4 * f_q + bb;
+    if (c < C && f <= F) pp[(size_t)c * (F + 1) + f] = sum;
   }
 }
 
@@ -640,6 +804,8 @@ TileMap make_tiles(const PixGeo& g, int B) {
   tm.tiles_per_row = (g.W_in + TILE - 1) / TILE;
   const long total = (long)B * g.R_in * tm.tiles_per_row;
   tm.total = total < 0x7fffffffL ? (int)total : -1;
+  tm.by_tpr.init((unsigned)tm.tiles_per_row);
+  tm.by_rows.init((unsigned)g.R_in);
   return tm;
 }
 
@@ -821,6 +987,43 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
   if (C * FQ > LB_ITEMS * LB_THREADS) {
     set_error("fno_lift_bwd: %d channels x %d features exceeds the per-CTA output tile", C, F);
     return FNO_E_ARG;
+  }
+  const TileMap tm0 = make_tiles(g, B);
+  if (tm0.total <= 0) { set_error("fno_lift_bwd: too many pixel tiles"); return FNO_E_ARG; }
+  float* part0 = static_cast<float*>(work);
+  {
+    // register-tiled form: contiguous 16-byte loads of the x tile need T * V % 4 == 0
+    const int CQ = (C + 3) / 4, nitems = CQ * FQ, NIT = (nitems + 31) / 32;
+    const bool aligned = (reinterpret_cast<size_t>(x) & 15) == 0;
+    if ((T * V) % 4 == 0 && aligned && NIT <= 2 && C * (TILE / 2) <= 3 * LB2_THREADS && TILE * (T * V / 4) <= 2 * LB2_THREADS && TILE * G <= LB2_THREADS &&
+        Wp % 2 == 0 && (reinterpret_cast<size_t>(dh) & 7) == 0) {
+      const size_t tile_bytes = sizeof(float) * ((size_t)TILE * FQ * 4 + (size_t)CQ * 4 * TP);
+      const size_t red_bytes = sizeof(float) * (size_t)(LB2_THREADS / 32) * nitems * 16;
+      const size_t smem2 = tile_bytes > red_bytes ? tile_bytes : red_bytes;
+      const int ctas = tm0.total < LB_CTAS ? tm0.total : LB_CTAS;
+      static std::atomic<int> done2{0};
+      if (!done2.load()) {
+        if (cudaFuncSetAttribute(lift_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(lift_bwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+          return check_launch("cudaFuncSetAttribute(lift_bwd2)");
+        done2.store(1);
+      }
+      if (smem2 <= 64 * 1024) {
+        if (NIT == 1) lift_bwd2_kernel<1><<<ctas, LB2_THREADS, smem2, st>>>(x, grid, stats, dh, part0, g, tm0, T, V, G, C);
+        else lift_bwd2_kernel<2><<<ctas, LB2_THREADS, smem2, st>>>(x, grid, stats, dh, part0, g, tm0, T, V, G, C);
+        count_launch();
+        int rc2 = check_launch("lift_bwd2_kernel");
+        if (rc2 != FNO_OK) return rc2;
+        ReduceSegs segs2;
+        for (int s = 0; s < 4; ++s) { segs2.dst[s] = nullptr; segs2.n[s] = 0; segs2.row[s] = 0; segs2.stride[s] = 0; segs2.col[s] = 0; }
+        segs2.dst[0] = gW0; segs2.n[0] = C * F; segs2.row[0] = F; segs2.stride[0] = F + 1; segs2.col[0] = 0;
+        segs2.dst[1] = gb0; segs2.n[1] = C;     segs2.row[1] = 1; segs2.stride[1] = F + 1; segs2.col[1] = F;
+        const int total_out2 = C * F + C;
+        partial_reduce_kernel<<<(total_out2 * 32 + 127) / 128, 128, 0, st>>>(part0, ctas, C * (F + 1), segs2);
+        count_launch();
+        return check_launch("partial_reduce_kernel(lift)");
+      }
+    }
   }
   const size_t smem = sizeof(float) * ((size_t)C * TP + (size_t)FQ * 4 * TP);
   static std::atomic<int> done{0};

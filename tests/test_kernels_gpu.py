@@ -250,6 +250,12 @@ LIFT_CASES = [
     ((4, 5, 6), 2, 3, 6),
     ((6, 6, 10), 3, 5, 20),      # V = 5 (cfg 4 channel count)
     ((12, 10), 2, 1, 32),
+    # T * V % 4 == 0: the register-tiled backward (lift_bwd2_kernel)
+    ((8, 128), 10, 2, 20),       # cfg-1 row: two full 64-pixel tiles per row
+    ((13, 70), 4, 2, 20),        # ragged second tile (6 valid pixels)
+    ((4, 4, 64), 4, 3, 12),      # 3-D: three grid features, 12 channels
+    ((20, 40), 2, 2, 40),        # two items per lane
+    ((10, 10), 8, 4, 64),        # output tile too large for the register-tiled form: first form
 ]
 
 
