@@ -73,7 +73,9 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
   unsigned long long* d_free = bars + 4;           // [2]
   unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 6);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp index made provably warp-uniform (role branches non-divergent for the compiler: the MMA warp then
+  // issues back-to-back UTCHMMAs from uniform registers, see tc_common.cuh)
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(a_ready + s, TCF_EPI_WARPS);
@@ -105,30 +107,29 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
   const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   if (warp == TCF_EPI_WARPS) {
-    // ---- MMA issuer -------------------------------------------------------------------------------
+    // ---- MMA issuer: the whole warp stays converged, one elected lane issues ---------------------------
     constexpr unsigned idesc = umma_idesc_tf32(TC_M, TC_HID, /*A K-major*/ 0, /*B K-major*/ 0);
+    const unsigned long long d_a_h = umma_desc(a_hi, 128, 1024), d_a_l = umma_desc(a_lo, 128, 1024);
+    const unsigned long long d_w_h = umma_desc(w_hi, 128, 1024), d_w_l = umma_desc(w_lo, 128, 1024);
     for (int it = 0; it < ntl; ++it) {
       const int st = it & 1;
       const unsigned ph = (unsigned)(it >> 1) & 1u;
       mbar_wait(a_ready + st, ph);
       mbar_wait(d_free + st, ph ^ 1u);
       tc_fence_after();
-      if (lane == 0) {
-        unsigned acc = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {          // lo*hi, hi*lo, hi*hi
-          const unsigned char* A = ((pass == 0) ? a_lo : a_hi) + st * A_BYTES;
-          const unsigned char* Bm = (pass == 1) ? w_lo : w_hi;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            // K = 8 per instruction = two 16-byte chunks: +256 B per K step for both operands
-            tc_mma_tf32(tmem_base + (unsigned)st * TC_HID, umma_desc(A + ks * 256, 128, 1024),
-                        umma_desc(Bm + ks * 256, 128, 1024), idesc, acc);
-            acc = 1;
-          }
-        }
-        tc_commit(d_full + st);
-      }
       __syncwarp();
+      const unsigned long long so = (unsigned long long)(st * (A_BYTES >> 4));
+      const unsigned d = tmem_base + (unsigned)st * TC_HID;
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass)              // lo*hi, hi*lo, hi*hi
+#pragma unroll
+        for (int ks = 0; ks < TC_KP / 8; ++ks) {
+          // K = 8 per instruction = two 16-byte chunks: +256 B per K step for both operands
+          if (ks < ksteps)
+            tc_mma_tf32_elect(d, (pass == 0 ? d_a_l : d_a_h) + so + (unsigned long long)(ks * (256 >> 4)),
+                              (pass == 1 ? d_w_l : d_w_h) + (unsigned long long)(ks * (256 >> 4)), idesc, (pass | ks) != 0);
+        }
+      tc_commit_elect(d_full + st);
     }
   } else {
     // ---- loader / epilogue warps ------------------------------------------------------------------

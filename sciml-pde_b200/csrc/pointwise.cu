@@ -76,7 +76,7 @@ pointwise_kernel(const float* __restrict__ in, const float* __restrict__ Wm, con
 // channels fetched in bursts of PW_CH loads that are all issued before the first FMA consumes
 // them -- 16 resident warps per SM each with PW_CH x 8 bytes in flight cover the HBM latency that
 // the one-load-at-a-time loop above exposes (profiles/r1_b: 183 registers, 12 % occupancy).
-constexpr int PW_CH = 10;
+constexpr int PW_CH = 20;
 
 template <int OT, bool TRANSPOSE>
 __global__ void __launch_bounds__(256, 2)
