@@ -49,6 +49,16 @@ int fno_sm_arch(void);                         /* 100: the only architecture com
 const char* fno_last_error(void);              /* thread-local, never NULL */
 unsigned long long fno_launch_count(void);     /* kernels launched by this library so far */
 void fno_shutdown(void);                       /* destroys every live plan */
+/* Arithmetic mode of the tensor-core kernels (process-wide, read at launch).  FNO_MATH_FP32 (default):
+ * every tcgen05.mma operand is split hi + lo and three MMAs accumulate lo*hi + hi*lo + hi*hi ("3xTF32"):
+ * results within the fp32-mode tolerance (<= 1e-5 relative).  FNO_MATH_TF32: a single kind::tf32 pass
+ * (10-bit mantissa operands, fp32 accumulate); stated bound <= 2e-3 relative on the projection head's
+ * outputs and gradients (tests/test_kernels_gpu.py::test_head_tf32_mode).  The FP32 CUDA-core kernels
+ * are not affected.  Returns the previous mode, or a negative error code.                          */
+#define FNO_MATH_FP32 0
+#define FNO_MATH_TF32 1
+int fno_set_math_mode(int mode);
+int fno_get_math_mode(void);
 
 /* ---- plans: immutable twiddle tables for one transform geometry ---------------------------- */
 /* 2-D plane [H, W], modes (m1, m2); requires 2*m1 <= H, m2 <= W/2+1, m1 <= 32.              */
@@ -175,6 +185,16 @@ int fno_head_bwd_tc(const float* h, const float* dout, const float* W1, const fl
                     const float* W2, const float* stats, float* dh, float* gW1, float* gb1,
                     float* gW2, float* gb2, void* work, int B, int R_in, int W_in, int R_out, int Wp,
                     int C, int HID, int V, fno_stream_t stream);
+
+/* ---- device-resident windowed dataset ----------------------------------------- */
+/* Replaces the per-item HDF5 read + host-side slicing of the reference loaders
+ * (fno/utils_2d_rd_baseline.py:59-102): traj [n_traj, pixels, T, V] stays on the GPU (time-inner), item b of
+ * a batch is (traj_idx[b], t_start[b]) (both device arrays) and one copy kernel writes
+ *   xx [B, pixels, initial_step, V] = traj[traj_idx[b], :, t_start[b] : +initial_step, :]
+ *   yy [B, pixels, rollout, V]      = traj[traj_idx[b], :, t_start[b]+initial_step : +rollout, :]     */
+int fno_window_gather(const float* traj, const long long* traj_idx, const int* t_start, float* xx,
+                      float* yy, int B, long npix, int T, int V, int initial_step, int rollout,
+                      fno_stream_t stream);
 
 /* ---- step tail: loss, gradient clipping, Adam, LR schedule --------------------- */
 /* nrmse(out, target).mean() of fno/train.py:34-40,:266-267 for out / target [B, P, V] (P = pixels x

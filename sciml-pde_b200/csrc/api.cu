@@ -11,6 +11,7 @@
 namespace fno {
 
 std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_math_mode{0};
 
 namespace {
 thread_local char t_err[512] = "";
@@ -211,6 +212,11 @@ int fno_version(void) { return 100; }
 int fno_sm_arch(void) { return 100; }
 const char* fno_last_error(void) { return t_err; }
 unsigned long long fno_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int fno_set_math_mode(int mode) {
+  if (mode != FNO_MATH_FP32 && mode != FNO_MATH_TF32) { set_error("fno_set_math_mode: unknown mode %d", mode); return FNO_E_ARG; }
+  return g_math_mode.exchange(mode);
+}
+int fno_get_math_mode(void) { return g_math_mode.load(); }
 
 void fno_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_plan_mutex);

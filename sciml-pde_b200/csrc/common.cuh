@@ -40,6 +40,7 @@ struct Plan {
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 extern std::atomic<unsigned long long> g_launches;
+extern std::atomic<int> g_math_mode;     // FNO_MATH_FP32 (3xTF32 split) / FNO_MATH_TF32 (single pass)
 inline void count_launch(unsigned n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // ---- kernel launchers (one per translation unit) -------------------------------------------

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1)
 head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, const float* __restrict__ W1,
                    const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ stats,
                    float* __restrict__ dh, float* __restrict__ rec, BtGeo g, int C, int V, int tiles_per_sample,
-                   int total_tiles) {
+                   int total_tiles, int single) {
   extern __shared__ __align__(128) unsigned char bsm[];
   unsigned char* aw1_hi = bsm;
   unsigned char* aw1_lo = aw1_hi + AW1_BYTES;
@@ -176,8 +176,10 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       for (int pass = 0; pass < 3; ++pass)              // lo*hi, hi*lo, hi*hi
 #pragma unroll
         for (int ks = 0; ks < BT_KC / 8; ++ks)
-          tc_mma_tf32_elect(d, (pass == 0 ? d_aw1_l : d_aw1_h) + (unsigned long long)(ks * (256 >> 4)),
-                            (pass == 1 ? d_bh_l : d_bh_h) + so + (unsigned long long)(ks * (256 >> 4)), idesc_a, (pass | ks) != 0);
+          if (pass == 2 || !single)                     // tf32 mode: the hi*hi pass alone
+            tc_mma_tf32_elect(d, (pass == 0 ? d_aw1_l : d_aw1_h) + (unsigned long long)(ks * (256 >> 4)),
+                              (pass == 1 ? d_bh_l : d_bh_h) + so + (unsigned long long)(ks * (256 >> 4)), idesc_a,
+                              single ? (unsigned)(ks != 0) : (unsigned)((pass | ks) != 0));
       tc_commit_elect(d1_full + s);
       tc_commit_elect(bh_free + s);
     };
@@ -193,17 +195,20 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
         for (int ks = 0; ks < BT_HID / 8; ++ks)
-          tc_mma_tf32_elect(tmem_base + TM_D2 + (unsigned)(s * 32), (pass == 0 ? d_a2_l : d_a2_h) + (unsigned long long)(ks * (2 * A2_LBO >> 4)),
-                            (pass == 1 ? d_b2_l : d_b2_h) + (unsigned long long)(ks * (256 >> 4)), idesc_b, (pass | ks) != 0);
+          if (pass == 2 || !single)
+            tc_mma_tf32_elect(tmem_base + TM_D2 + (unsigned)(s * 32), (pass == 0 ? d_a2_l : d_a2_h) + (unsigned long long)(ks * (2 * A2_LBO >> 4)),
+                              (pass == 1 ? d_b2_l : d_b2_h) + (unsigned long long)(ks * (256 >> 4)), idesc_b,
+                              single ? (unsigned)(ks != 0) : (unsigned)((pass | ks) != 0));
       const unsigned long long so = (unsigned long long)(s * (B3_BYTES >> 4));
       const unsigned at = tmem_base + TM_D1 + (unsigned)s * 128u;       // dpre^T hi at +0, lo at +64
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass)
 #pragma unroll
         for (int ks = 0; ks < BT_PX / 8; ++ks)
-          tc_mma_tf32_ts_elect(tmem_base + TM_D3, at + (unsigned)((pass == 0 ? 64 : 0) + ks * 8),
-                               (pass == 1 ? d_b3_l : d_b3_h) + so + (unsigned long long)(ks * (2 * B3_LBO >> 4)), idesc_c,
-                               (unsigned)((pass | ks) != 0) | (unsigned)(it > 0));
+          if (pass == 2 || !single)
+            tc_mma_tf32_ts_elect(tmem_base + TM_D3, at + (unsigned)((pass == 0 ? 64 : 0) + ks * 8),
+                                 (pass == 1 ? d_b3_l : d_b3_h) + so + (unsigned long long)(ks * (2 * B3_LBO >> 4)), idesc_c,
+                                 (single ? (unsigned)(ks != 0) : (unsigned)((pass | ks) != 0)) | (unsigned)(it > 0));
       tc_commit_elect(bc_done);
       tc_commit_elect(d2_full + s);
       TRACE(2);
@@ -250,7 +255,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       }
       // dpre^T for (c) goes back into tensor memory, over the pre^T values this thread just read
       tmem_st16(tq, hi);
-      tmem_st16(tq + 64u, lo);
+      if (!single) tmem_st16(tq + 64u, lo);
       __syncwarp();
       if (lane == 0) mbar_arrive(g_free + s);
       if (warp == 0) TRACE(9);
@@ -261,7 +266,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       for (int p = 0; p < 16; ++p) {
         const int off = a2off + (p & 7) * 16 + (p >> 3) * A2_SBO;
         *reinterpret_cast<float*>(a2_hi + off) = hi[p];
-        *reinterpret_cast<float*>(a2_lo + off) = lo[p];
+        if (!single) *reinterpret_cast<float*>(a2_lo + off) = lo[p];
       }
       tmem_st_wait();
       fence_proxy_async();
@@ -392,7 +397,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       for (int u = 0; u < 2; ++u) {
         const int off = s * BH_BYTES + (px & 7) * 16 + (px >> 3) * BH_SBO + (kq + 3 * u) * 128;
         *reinterpret_cast<float4*>(bh_hi + off) = make_float4(hi[u][0], hi[u][1], hi[u][2], hi[u][3]);
-        *reinterpret_cast<float4*>(bh_lo + off) = make_float4(lo[u][0], lo[u][1], lo[u][2], lo[u][3]);
+        if (!single) *reinterpret_cast<float4*>(bh_lo + off) = make_float4(lo[u][0], lo[u][1], lo[u][2], lo[u][3]);
       }
       if (kq == 0) {
         mbar_wait(g_free + s, phf);
@@ -426,7 +431,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
           const int c = 4 * (kq + 3 * u) + e;
           const int off = s * B3_BYTES + (c & 7) * 16 + (c >> 3) * B3_SBO + (px >> 2) * B3_LBO + (px & 3) * 4;
           *reinterpret_cast<float*>(b3_hi + off) = hi[u][e];
-          *reinterpret_cast<float*>(b3_lo + off) = lo[u][e];
+          if (!single) *reinterpret_cast<float*>(b3_lo + off) = lo[u][e];
         }
       fence_proxy_async();
       __syncwarp();
@@ -538,10 +543,11 @@ extern "C" int fno_head_bwd_tc(const float* h, const float* dout, const float* W
   }
   const int ctas = (int)(total < 148 ? total : 148);
   float* rec = static_cast<float*>(work);
+  const int single = g_math_mode.load() == FNO_MATH_TF32;
   if (V <= 2)
-    head_bwd_tc_kernel<2><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total);
+    head_bwd_tc_kernel<2><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
   else
-    head_bwd_tc_kernel<4><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total);
+    head_bwd_tc_kernel<4><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
   count_launch();
   rc = check_launch("head_bwd_tc_kernel");
   if (rc != FNO_OK) return rc;

@@ -58,7 +58,7 @@ constexpr int TCF_MAXCH = 2;               // 16-byte channel chunks staged per 
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
                    const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
-                   float* __restrict__ out, HeadGeo g, int C, int V, int tiles_per_sample, int total_tiles) {
+                   float* __restrict__ out, HeadGeo g, int C, int V, int tiles_per_sample, int total_tiles, int single) {
   extern __shared__ __align__(128) unsigned char tsm[];
   unsigned char* a_hi = tsm;                       // [2 stages][A_BYTES]
   unsigned char* a_lo = a_hi + 2 * A_BYTES;
@@ -125,9 +125,10 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
 #pragma unroll
         for (int ks = 0; ks < TC_KP / 8; ++ks) {
           // K = 8 per instruction = two 16-byte chunks: +256 B per K step for both operands
-          if (ks < ksteps)
+          if (ks < ksteps && (pass == 2 || !single))     // tf32 mode: the hi*hi pass alone
             tc_mma_tf32_elect(d, (pass == 0 ? d_a_l : d_a_h) + so + (unsigned long long)(ks * (256 >> 4)),
-                              (pass == 1 ? d_w_l : d_w_h) + (unsigned long long)(ks * (256 >> 4)), idesc, (pass | ks) != 0);
+                              (pass == 1 ? d_w_l : d_w_h) + (unsigned long long)(ks * (256 >> 4)), idesc,
+                              single ? (unsigned)(ks != 0) : (unsigned)((pass | ks) != 0));
         }
       tc_commit_elect(d_full + st);
     }
@@ -167,7 +168,7 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
 #pragma unroll
           for (int e = 0; e < 4; ++e) split_tf32(raw[u][e], hi[e], lo[e]);
           *reinterpret_cast<float4*>(a_hi + st * A_BYTES + abase + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(a_lo + st * A_BYTES + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+          if (!single) *reinterpret_cast<float4*>(a_lo + st * A_BYTES + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
       fence_proxy_async();
@@ -271,7 +272,8 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
     done.store(1);
   }
   const int ctas = (int)(total < 148 ? total : 148);
-  head_fwd_tc_kernel<<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total);
+  head_fwd_tc_kernel<<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total,
+                                                      g_math_mode.load() == FNO_MATH_TF32);
   count_launch();
   return check_launch("head_fwd_tc_kernel");
 }

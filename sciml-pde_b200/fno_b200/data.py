@@ -88,3 +88,75 @@ class SyntheticWindows(torch.utils.data.Dataset):
 
 def windows_of(traj, initial_step, rollout=1):
     return windows(traj, initial_step, rollout)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Device-resident windowed dataset
+# ---------------------------------------------------------------------------------------------------
+def epoch_indices(n_items: int, batch: int, shuffle: bool, seed: int, epoch: int = 0, rank: int = 0, world: int = 1):
+    """Host-side index plan of one epoch: the global order (a seeded ``torch.randperm`` when shuffling, as a
+    ``DataLoader(shuffle=True)`` with a seeded generator draws it), cut into global batches of ``batch`` items
+    with the last one ragged (``drop_last=False``, fno/train.py:95-97); under data parallelism rank r takes the
+    rank-strided slice of every global batch, so the union over ranks is the single-GPU batch.
+    Returns a list of 1-D int64 tensors (this rank's items per step; possibly empty for a ragged tail)."""
+    if n_items <= 0 or batch <= 0 or world <= 0 or not 0 <= rank < world:
+        raise ValueError("epoch_indices: bad arguments")
+    if shuffle:
+        g = torch.Generator().manual_seed(seed + epoch)
+        order = torch.randperm(n_items, generator=g)
+    else:
+        order = torch.arange(n_items)
+    return [order[s:s + batch][rank::world].contiguous() for s in range(0, n_items, batch)]
+
+
+class DeviceWindows:
+    """Trajectories cached on the GPU, sliding windows gathered on the device (one copy kernel per batch).
+
+    Replaces ``FNODatasetMult`` + ``DataLoader`` of the reference (fno/utils_2d_rd_baseline.py:59-102,
+    fno/train.py:95-97): item ``i`` is window ``i % n_windows`` of trajectory ``i // n_windows`` -- the order
+    ``SyntheticWindows`` / the reference loaders use -- and yields ``xx [*sp, initial_step, V]``,
+    ``yy [*sp, rollout, V]``, ``grid [*sp, nd]``.  ``traj`` is ``[n_traj, T, *spatial, V]`` (PDEBench layout);
+    it is stored once, time-inner, in device memory (180 GB of HBM3e holds ~270 full cfg-1 trajectories
+    per GPU; shard trajectories across ranks beyond that)."""
+
+    def __init__(self, traj: torch.Tensor, initial_step: int = 10, rollout: int = 1, device=None,
+                 grid_lo: float = -1.0, grid_hi: float = 1.0):
+        if traj.dim() < 4:
+            raise ValueError("DeviceWindows: traj must be [n_traj, T, *spatial, V]")
+        device = torch.device(device if device is not None else "cuda")
+        self.spatial = tuple(traj.shape[2:-1])
+        self.nd = len(self.spatial)
+        self.T, self.V = traj.shape[1], traj.shape[-1]
+        self.initial_step, self.rollout = initial_step, rollout
+        self.n_windows = self.T - initial_step - rollout + 1
+        if self.n_windows <= 0:
+            raise ValueError("DeviceWindows: trajectories shorter than initial_step + rollout")
+        n_traj = traj.shape[0]
+        perm = (0,) + tuple(range(2, 2 + self.nd)) + (1, 2 + self.nd)          # -> [n, *sp, T, V]
+        self.traj = traj.to(device=device, dtype=torch.float32).permute(*perm).contiguous().view(n_traj, -1, self.T, self.V)
+        lins = [torch.linspace(grid_lo + (grid_hi - grid_lo) / (2 * n), grid_hi - (grid_hi - grid_lo) / (2 * n), n)
+                for n in self.spatial]                                           # cell centres per axis
+        self.grid = torch.stack(torch.meshgrid(*lins, indexing="ij"), dim=-1).to(device)
+        self.device = device
+
+    def __len__(self):
+        return self.traj.shape[0] * self.n_windows
+
+    def batch(self, items: torch.Tensor):
+        """items: 1-D int64 (host or device) -> (xx [B,*sp,T0,V], yy [B,*sp,R,V], grid [B,*sp,nd]) on the device."""
+        from . import lib
+
+        items = items.to(device=self.device, dtype=torch.int64)
+        ti = torch.div(items, self.n_windows, rounding_mode="floor")
+        ts = (items - ti * self.n_windows).to(torch.int32)
+        xx, yy = lib.window_gather(self.traj, ti.contiguous(), ts.contiguous(), self.initial_step, self.rollout)
+        B = items.numel()
+        xx = xx.view((B,) + self.spatial + (self.initial_step, self.V))
+        yy = yy.view((B,) + self.spatial + (self.rollout, self.V))
+        return xx, yy, self.grid.unsqueeze(0).expand(B, *([-1] * (self.nd + 1)))
+
+    def epoch(self, batch: int, shuffle: bool = True, seed: int = 16, epoch: int = 0, rank: int = 0, world: int = 1):
+        """Iterates this rank's batches of one epoch (see ``epoch_indices``)."""
+        for items in epoch_indices(len(self), batch, shuffle, seed, epoch, rank, world):
+            if items.numel():
+                yield self.batch(items)

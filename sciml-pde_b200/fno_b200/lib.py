@@ -53,6 +53,9 @@ def load():
             "fno_shutdown": (None, []),
             "fno_plan2d_create": (i, [i, i, i, i, i, vpp]),
             "fno_plan3d_create": (i, [i, i, i, i, i, i, i, vpp]),
+            "fno_window_gather": (i, [vp, vp, vp, vp, vp, i, l, i, i, i, i, vp]),
+            "fno_set_math_mode": (i, [i]),
+            "fno_get_math_mode": (i, []),
             "fno_plan_destroy": (i, [vp]),
             "fno_plan_workspace_bytes": (C.c_size_t, [vp, l]),
             "fno_sc2d_fwd_transform": (i, [vp, vp, vp, vp, vp, l, i, f, vp]),
@@ -97,6 +100,7 @@ K1_TENSOR_CORES = os.environ.get("FNO_K1_TC", "0") == "1"
 
 EXPORTED_SYMBOLS = (
     "fno_version", "fno_sm_arch", "fno_last_error", "fno_launch_count", "fno_shutdown",
+    "fno_set_math_mode", "fno_get_math_mode", "fno_window_gather",
     "fno_plan2d_create", "fno_plan3d_create", "fno_plan_destroy", "fno_plan_workspace_bytes",
     "fno_sc2d_fwd_transform", "fno_sc2d_fwd_workspace_bytes", "fno_sc2d_fwd_transform_ws",
     "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
@@ -423,6 +427,24 @@ def lift_bwd(geo: TrunkGeo, x, grid, stats, dh, W0_shape):
     return gW0, gb0
 
 
+MATH_MODES = {"fp32": 0, "tf32": 1}
+
+
+def set_math_mode(mode: str) -> str:
+    """Arithmetic mode of the tensor-core kernels: "fp32" (3xTF32 split, <= 1e-5 relative; default) or
+    "tf32" (single kind::tf32 pass, stated bound <= 2e-3 relative).  Returns the previous mode."""
+    if mode not in MATH_MODES:
+        raise FnoError(f"unknown math mode {mode!r} (expected one of {sorted(MATH_MODES)})")
+    prev = load().fno_set_math_mode(MATH_MODES[mode])
+    if prev < 0:
+        _check(prev, "fno_set_math_mode")
+    return {v: k for k, v in MATH_MODES.items()}[prev]
+
+
+def get_math_mode() -> str:
+    return {v: k for k, v in MATH_MODES.items()}[load().fno_get_math_mode()]
+
+
 def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
     for t, n in ((h, "h"), (W1, "fc1.weight"), (b1, "fc1.bias"), (W2, "fc2.weight"), (b2, "fc2.bias"),
                  (stats, "stats")):
@@ -457,3 +479,20 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
               gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
            "fno_head_bwd_tc" if tc else "fno_head_bwd")
     return dh, gW1, gb1, gW2, gb2
+
+
+def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Tensor, initial_step: int, rollout: int):
+    """traj [n_traj, pixels, T, V] (device, time-inner) -> xx [B, pixels, initial_step, V], yy [B, pixels, rollout, V]
+    for the items (traj_idx[b], t_start[b]); one copy kernel, nothing touches the host."""
+    _require(traj, torch.float32, "traj")
+    if traj.dim() != 4 or traj_idx.dtype != torch.int64 or t_start.dtype != torch.int32 or \
+            traj_idx.device != traj.device or t_start.device != traj.device or traj_idx.shape != t_start.shape:
+        raise FnoError("window_gather: traj [n, pixels, T, V] f32, traj_idx int64 [B], t_start int32 [B], one device")
+    n, npix, T, V = traj.shape
+    B = traj_idx.numel()
+    xx = torch.empty((B, npix, initial_step, V), dtype=torch.float32, device=traj.device)
+    yy = torch.empty((B, npix, rollout, V), dtype=torch.float32, device=traj.device)
+    _check(load().fno_window_gather(traj.data_ptr(), traj_idx.data_ptr(), t_start.data_ptr(), xx.data_ptr(),
+                                    yy.data_ptr(), B, npix, T, V, initial_step, rollout, _stream()),
+           "fno_window_gather")
+    return xx, yy

@@ -93,3 +93,26 @@ def test_dp_bucket_order():
     assert [g[0].split(".")[0] for g in groups] == ["fc1", "conv3", "conv2", "conv1", "fc0"]
     flat = [n for g in groups for n in g]
     assert sorted(flat) == sorted(n for n, _ in m.named_parameters())
+
+
+def test_epoch_indices_shard_every_global_batch_rank_strided():
+    """Host logic of the device-resident dataset (fno_b200/data.py): N ranks at global batch G draw exactly the
+    single-GPU batches, split rank-strided, ragged tail kept (drop_last=False)."""
+    import torch
+
+    from fno_b200 import data
+
+    single = data.epoch_indices(23, 8, True, 16)
+    assert [len(b) for b in single] == [8, 8, 7]
+    assert sorted(torch.cat(single).tolist()) == list(range(23))
+    for world in (2, 4):
+        parts = [data.epoch_indices(23, 8, True, 16, 0, r, world) for r in range(world)]
+        for step, whole in enumerate(single):
+            merged = torch.stack([p[step] for p in parts if len(p[step]) == len(parts[0][step])], dim=1).flatten().tolist() \
+                if all(len(p[step]) == len(parts[0][step]) for p in parts) else None
+            union = sorted(torch.cat([p[step] for p in parts]).tolist())
+            assert union == sorted(whole.tolist())
+            if merged is not None:
+                assert merged == whole.tolist()           # rank-strided: interleaving the ranks restores the order
+    assert data.epoch_indices(23, 8, False, 0)[0].tolist() == list(range(8))
+    assert data.epoch_indices(23, 8, True, 16, 1)[0].tolist() != single[0].tolist()   # next epoch reshuffles
