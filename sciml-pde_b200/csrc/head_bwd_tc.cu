@@ -25,8 +25,8 @@
 // profiles/r1_h): every byte that stays in TMEM or is not restaged counts.
 //
 // Warp roles (persistent CTA, one per SM): 16 epilogue warps (4 lane quadrants x 4 pixel quarters),
-// 1 MMA-issue warp, 6 loader warps (global -> split -> operand buffers; four of them also drain the dh
-// accumulator to global memory).  mbarrier hand-offs; operand slots, the pre^T / dpre^T tile and the dh
+// 1 MMA-issue warp, 6 loader warps (global -> split -> operand buffers); the dh accumulator is drained to
+// global memory by the epilogue warps in rotation.  mbarrier hand-offs; operand slots, the pre^T / dpre^T tile and the dh
 // accumulator are double-buffered so the (a) MMAs of tile i+1 run under the GELU epilogue of tile i.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -229,6 +229,40 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       aw2[v] = 0.f;
     }
     const int a2off = (2 * colq) * A2_SBO + (j >> 2) * A2_LBO + (j & 3) * 4;
+    // dh tile of tile `t` (accumulator slot t & 1): D2 row i lives in lane 32 (i / 16) + i % 16, so the drain
+    // needs one warp per lane quadrant; the duty rotates over the four pixel-quarter groups (tile t is drained
+    // by the warps with colq == t % 4) so that it costs every epilogue warp the same ~5 %.  A loader warp is a
+    // single dependent instruction stream and was the kernel's bottleneck when it also carried the drain.
+    const int npix = (int)g.npix;
+    const size_t sample_stride = (size_t)C * g.plane;
+    auto drain_dh = [&](int t) {
+      const int s = t & 1;
+      tc_fence_after();
+      const unsigned ta = tmem_base + ((unsigned)(quad * 32) << 16) + TM_D2 + (unsigned)(s * 32);
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b = (int)g.by_tps.div((unsigned)tile);
+      const int p = (tile - b * tiles_per_sample) * BT_PX + 16 * quad + lane;
+      const bool ok = lane < 16 && p < npix;
+      const int row = (int)g.by_w.div((unsigned)(ok ? p : 0));
+      float* __restrict__ dp = dh + (size_t)b * sample_stride + (size_t)(row * g.Wp + ((ok ? p : 0) - row * g.W_in));
+#pragma unroll
+      for (int c0 = 0; c0 < BT_KC; c0 += 8) {
+        float v[8];
+        tmem_ld8(ta + (unsigned)c0, v);
+        if (c0 + 8 == BT_KC) {                     // accumulator fully read
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(d2_free + s);
+        }
+        if (ok) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c0 + c < C) *dp = v[c];
+            dp += g.plane;
+          }
+        }
+      }
+    };
     for (int it = 0; it < ntl; ++it) {
       const int s = it & 1;
       const unsigned ph = ((unsigned)it >> 1) & 1u;
@@ -274,6 +308,12 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       __syncwarp();
       if (lane == 0) mbar_arrive(a23_ready);
       if (warp == 0) TRACE(11);
+      // (b), (c) of tile it-1 are done (bc_done above): its dh accumulator is complete
+      if (it > 0 && colq == ((it - 1) & 3)) drain_dh(it - 1);
+    }
+    if (colq == ((ntl - 1) & 3)) {
+      mbar_wait(bc_done, (unsigned)(ntl - 1) & 1u);
+      drain_dh(ntl - 1);
     }
     // partial records: gW2 share of this pixel quarter; the gW1 | gb1 accumulator (quarter 0 warps)
 #pragma unroll
@@ -288,17 +328,15 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
         *reinterpret_cast<float4*>(myrec + REC_W1 + j * BT_NC + c) = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
     }
   } else {
-    // ---- loaders: global -> split -> operand buffers; warps 0-3 of the group also drain dh ------------
+    // ---- loaders: global -> split -> operand buffers -------------------------------------------------
     // A loader warp is a single dependent instruction stream whose shared-memory stores queue behind the
     // epilogue's, so its work is ordered by urgency and runs a tile ahead: per iteration the (a) operands of
-    // tile it+1 (their slot is free as soon as the (a) MMAs of tile it-1 are done), then the dh drain of tile
-    // it-1, then h^T of tile it+1 (its slot is free when the (c) MMAs of tile it-1 are done), then the global
-    // loads of tile it+3.
+    // tile it+1 (their slot is free as soon as the (a) MMAs of tile it-1 are done), then h^T of tile it+1 (its
+    // slot is free when the (c) MMAs of tile it-1 are done), then the global loads of tile it+3.
     const int lt = tid - BT_LD_WARP0 * 32;
     const int lw = lt >> 5;
     const int px = lt & (BT_PX - 1);
     const int kq = lt >> 6;                        // stages the 4-channel chunks kq and kq + 3
-    const int dq = warp & 3;                       // TMEM lane quadrant this warp may read
     const int npix = (int)g.npix;
     const size_t sample_stride = (size_t)C * g.plane;
     float gb2[BT_GV] = {0.f, 0.f, 0.f, 0.f};
@@ -346,40 +384,6 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
     // masked / padded channel values of a raw set
     auto chan = [&](const Raw& r, int u, int e) -> float {
       return ((creal >> (4 * u + e)) & 1u) ? (r.valid ? r.x[u][e] : 0.f) : (((cone >> (4 * u + e)) & 1u) ? 1.f : 0.f);
-    };
-    auto drain_dh = [&](int it) {                  // dh tile of tile `it`: D2 row i lives in lane 32 (i / 16) + i % 16
-      const int s = it & 1;
-      if (lw == 0) TRACE(22);
-      mbar_wait(d2_full + s, ((unsigned)it >> 1) & 1u);
-      tc_fence_after();
-      if (lw == 0) TRACE(23);
-      // 8 columns at a time: the drain runs inside the loader warps, whose two raw sets are live
-      const unsigned ta = tmem_base + ((unsigned)(dq * 32) << 16) + TM_D2 + (unsigned)(s * 32);
-      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-      const int b = (int)g.by_tps.div((unsigned)tile);
-      const int p = (tile - b * tiles_per_sample) * BT_PX + 16 * dq + lane;
-      const bool ok = lane < 16 && p < npix;
-      const int row = (int)g.by_w.div((unsigned)(ok ? p : 0));
-      float* __restrict__ dp = dh + (size_t)b * sample_stride + (size_t)(row * g.Wp + ((ok ? p : 0) - row * g.W_in));
-#pragma unroll
-      for (int c0 = 0; c0 < BT_KC; c0 += 8) {
-        float v[8];
-        tmem_ld8(ta + (unsigned)c0, v);
-        if (c0 + 8 == BT_KC) {                     // accumulator fully read
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(d2_free + s);
-          if (lw == 0) TRACE(24);
-        }
-        if (ok) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            if (c0 + c < C) *dp = v[c];
-            dp += g.plane;
-          }
-        }
-      }
-      if (lw == 0) TRACE(25);
     };
     // operands of (a) for tile `it`: h [px][c] hi / lo, dout * std
     auto stage_a = [&](const Raw& r, int it) {
@@ -446,18 +450,17 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
     load_raw(ra, 2);
     // iteration `it` works on tile it+1 (raw set rb for even it, ra for odd it)
     for (int it = 0; it < ntl; it += 2) {
-      if (it + 1 < ntl) stage_a(rb, it + 1);
-      if (it > 0 && lw < 4) drain_dh(it - 1);
-      if (it + 1 < ntl) stage_c(rb, it + 1);
-      load_raw(rb, it + 3);
       if (it + 1 < ntl) {
-        if (it + 2 < ntl) stage_a(ra, it + 2);
-        if (lw < 4) drain_dh(it);
-        if (it + 2 < ntl) stage_c(ra, it + 2);
-        load_raw(ra, it + 4);
+        stage_a(rb, it + 1);
+        stage_c(rb, it + 1);
       }
+      load_raw(rb, it + 3);
+      if (it + 2 < ntl) {
+        stage_a(ra, it + 2);
+        stage_c(ra, it + 2);
+      }
+      load_raw(ra, it + 4);
     }
-    if (lw < 4) drain_dh(ntl - 1);
     if (kq == 0) {
 #pragma unroll
       for (int v = 0; v < BT_GV; ++v) myrec[REC_B2 + px * BT_GV + v] = gb2[v];
