@@ -169,7 +169,7 @@ class ClockSampler:
 class KernelTimer:
     """Wraps the fno_b200.lib call wrappers with CUDA events on the current stream."""
 
-    NAMES = ["fwd_transform", "inv_transform", "mix_fwd", "mix_bwd", "pointwise_fwd", "pointwise_wgrad",
+    NAMES = ["fwd_transform", "inv_transform", "mix_fwd", "mix_bwd", "pointwise_fwd", "pointwise_wgrad", "pointwise_bwd",
              "lift_stats", "lift_fwd", "lift_bwd", "head_fwd", "head_bwd"]
 
     def __init__(self, lib):
@@ -240,6 +240,7 @@ def algorithmic_bytes(tag: str, B: int) -> int:
         "pointwise_fwd": 2 * act,
         "pointwise_bwd_data": 2 * act,
         "pointwise_wgrad": 2 * act,
+        "pointwise_bwd": 3 * act,                                  # reads ds, a; writes dx (weight + data gradient)
         # lift / head: x = [B,128,128,10,2] (+grid [..,2]) in, h = act out; out/dout = [B,128,128,2]
         "lift_stats": 4 * B * RES * RES * CFG["initial_step"] * CFG["num_channels"],
         "lift_fwd": 4 * B * RES * RES * (CFG["initial_step"] * CFG["num_channels"] + 2) + act,

@@ -132,6 +132,12 @@ int fno_pointwise_fwd(const float* in, const float* W, const float* bias, float*
 size_t fno_pointwise_wgrad_workspace_bytes(int B, int Co, int Ci, long N);
 int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B,
                         int Co, int Ci, long N, fno_stream_t stream);
+/* Whole autograd of the 1x1 convolution in one call: gW, gb as above AND the data gradient
+ * dx [B, Ci, N] = W^T ds.  When the TMA-fed weight-gradient kernel can carry it (width <= 20, aligned
+ * tensors) dx is produced from the ds slabs already staged in shared memory -- ds is read once --;
+ * otherwise the call runs fno_pointwise_wgrad followed by fno_pointwise_fwd(transpose = 1).        */
+int fno_pointwise_bwd(const float* ds, const float* a, const float* W, float* dx, float* gW, float* gb,
+                      void* work, int B, int Co, int Ci, long N, fno_stream_t stream);
 
 /* ---- lift: per-sample normalisation + fc0, written into the trunk layout ------ */
 /* Trunk layout of an activation: h[b, c, r, w], r < R_out rows of pitch Wp floats per channel

@@ -289,8 +289,8 @@ wgrad_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, 
 
 // ------------------------------------------------------------------------------------------
 // v2 of the weight gradient: TMA-fed (cp.async.bulk, 1-D) slabs with an mbarrier full/empty ring.
-// A producer warp streams slab after slab -- one bulk copy of KT pixels per channel row of ds and
-// of a -- into a WG2_STAGES-deep ring; consumer warps each own one T x T output tile with lanes
+// Warp 0 streams slab after slab -- one bulk copy of KT pixels per channel row of ds and
+// of a -- into a WG2_STAGES-deep ring; the warps each own one T x T output tile with lanes
 // over pixel quads (LDS.128: 2T loads per 4 T^2 FMA).  Nothing but the bulk copies touches global
 // memory in the steady state, so the kernel streams at the HBM rate set by its 8 bytes/pixel/channel.
 // ------------------------------------------------------------------------------------------
@@ -299,16 +299,21 @@ constexpr int WG2_KT = 512;      // pixels per slab: 2 KB per bulk copy (the TMA
                                  // so 512-byte copies cap the stream at ~3 TB/s -- profiles/r1_d)
 constexpr int WG2_MAXW = 8;      // consumer warps per CTA
 
-template <int T>
-__global__ void __launch_bounds__(32 * (WG2_MAXW + 1))
+// DGRAD: the same pass also produces the bypass data gradient dx[b, i, p] = sum_o W[o, i] ds[b, o, p]
+// (autograd of nn.Conv2d(C, C, 1), fno/fno.py:162) from the ds slab that is already in shared memory --
+// one read of the ds tensor per layer instead of two.  Thread = two adjacent pixels of the 512-pixel slab
+// (8 consumer warps), all Ci outputs in registers, weight rows broadcast with LDS.128.
+template <int T, bool DGRAD>
+__global__ void __launch_bounds__(32 * WG2_MAXW)
 wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co,
                       int Ci, long N, int slabs_per_sample, long total_slabs, long slabs_per_cta, int tiles_i,
-                      int ntiles, int nwarps, int KH) {
+                      int ntiles, int nwarps, int KH, const float* __restrict__ Wm, float* __restrict__ dx) {
   extern __shared__ __align__(16) float sm[];   // WG2_STAGES x ([Co][KT] ds slab, [Ci][KT] a slab), then barriers
   constexpr int KT2 = WG2_KT;
   const int rows = Co + Ci;
   unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)WG2_STAGES * rows * KT2);
   unsigned long long* empty = full + WG2_STAGES;
+  float* ws = reinterpret_cast<float*>(empty + WG2_STAGES);     // DGRAD: W [Co][2T] (rows zero-padded)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
@@ -318,31 +323,40 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (DGRAD) {
+    for (int i = threadIdx.x; i < Co * 2 * T; i += blockDim.x) {
+      const int o = i / (2 * T), c = i - o * (2 * T);
+      ws[i] = (c < Ci) ? __ldg(Wm + (size_t)o * Ci + c) : 0.f;
+    }
+  }
   __syncthreads();
   long s_begin = (long)blockIdx.x * slabs_per_cta;
   long s_end = s_begin + slabs_per_cta;
   if (s_end > total_slabs) s_end = total_slabs;
 
-  if (warp == nwarps) {
-    // ---- producer warp ---------------------------------------------------------------------
-    for (long slab = s_begin; slab < s_end; ++slab) {
-      const int it = (int)(slab - s_begin);
-      const int stage = it % WG2_STAGES;
-      const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
-      mbar_wait(empty + stage, ph ^ 1u);
-      const long b = slab / slabs_per_sample;
-      const long k0 = (slab - b * slabs_per_sample) * KT2;
-      const long left = N - k0;
-      const unsigned bytes = (unsigned)((left < KT2 ? left : KT2) * sizeof(float));
-      float* dst = sm + (size_t)stage * rows * KT2;
-      if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes * (unsigned)rows);
-      __syncwarp();
-      for (int c = lane; c < rows; c += 32) {
-        const float* src = (c < Co) ? (ds + ((size_t)b * Co + c) * N + k0) : (a + ((size_t)b * Ci + (c - Co)) * N + k0);
-        bulk_g2s(dst + (size_t)c * KT2, src, bytes, full + stage);
-      }
+  // ---- producer duty (warp 0): one bulk copy per channel row of ds and of a per slab.  There is no
+  // dedicated producer warp: a ninth warp would put three warps on one SM sub-partition and cap the kernel at
+  // 168 registers (16 K registers per sub-partition), which the fused data-gradient phase does not fit.
+  auto produce = [&](long slab) {
+    if (slab >= s_end) return;
+    const int it = (int)(slab - s_begin);
+    const int stage = it % WG2_STAGES;
+    const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
+    mbar_wait(empty + stage, ph ^ 1u);            // every consumer warp is done with the slab that used this stage
+    const long b = slab / slabs_per_sample;
+    const long k0 = (slab - b * slabs_per_sample) * KT2;
+    const long left = N - k0;
+    const unsigned bytes = (unsigned)((left < KT2 ? left : KT2) * sizeof(float));
+    float* dst = sm + (size_t)stage * rows * KT2;
+    if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes * (unsigned)rows);
+    __syncwarp();
+    for (int c = lane; c < rows; c += 32) {
+      const float* src = (c < Co) ? (ds + ((size_t)b * Co + c) * N + k0) : (a + ((size_t)b * Ci + (c - Co)) * N + k0);
+      bulk_g2s(dst + (size_t)c * KT2, src, bytes, full + stage);
     }
-    return;
+  };
+  if (warp == 0) {
+    for (int s = 0; s < WG2_STAGES; ++s) produce(s_begin + s);
   }
 
   // ---- consumer warps: (tile, pixel part) each; a tile is a T x T block of outputs ------------
@@ -396,8 +410,35 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
         }
       }
     }
+    if (DGRAD) {
+      const int px = 2 * (int)threadIdx.x;       // 256 consumer threads x 2 pixels = one slab
+      if (px < left) {                            // `left` is a multiple of 4
+        const long k0 = (slab - b * slabs_per_sample) * KT2;
+        const float* dsp = sm + (size_t)stage * rows * KT2 + px;
+        float2 o2[2 * T];
+#pragma unroll
+        for (int i = 0; i < 2 * T; ++i) o2[i] = make_float2(0.f, 0.f);
+        for (int o = 0; o < Co; ++o) {
+          const float2 d = *reinterpret_cast<const float2*>(dsp + (size_t)o * KT2);
+          const float4* wrow = reinterpret_cast<const float4*>(ws + o * 2 * T);
+#pragma unroll
+          for (int q = 0; q < 2 * T / 4; ++q) {
+            const float4 w = wrow[q];
+            o2[4 * q + 0].x = fmaf(w.x, d.x, o2[4 * q + 0].x); o2[4 * q + 0].y = fmaf(w.x, d.y, o2[4 * q + 0].y);
+            o2[4 * q + 1].x = fmaf(w.y, d.x, o2[4 * q + 1].x); o2[4 * q + 1].y = fmaf(w.y, d.y, o2[4 * q + 1].y);
+            o2[4 * q + 2].x = fmaf(w.z, d.x, o2[4 * q + 2].x); o2[4 * q + 2].y = fmaf(w.z, d.y, o2[4 * q + 2].y);
+            o2[4 * q + 3].x = fmaf(w.w, d.x, o2[4 * q + 3].x); o2[4 * q + 3].y = fmaf(w.w, d.y, o2[4 * q + 3].y);
+          }
+        }
+        float* __restrict__ op = dx + (size_t)b * Ci * N + k0 + px;
+#pragma unroll
+        for (int i = 0; i < 2 * T; ++i)
+          if (i < Ci) *reinterpret_cast<float2*>(op + (size_t)i * N) = o2[i];
+      }
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
+    if (warp == 0) produce(slab + WG2_STAGES);    // refill the stage just released (waits for the other warps)
   }
   if (!has_tile) return;
   // part[(cta * KH + kh)][Co][Ci + 1]
@@ -483,8 +524,11 @@ extern "C" size_t fno_pointwise_wgrad_workspace_bytes(int B, int Co, int Ci, lon
   return sizeof(float) * (size_t)WG_CTAS * Co * (Ci + 1);
 }
 
-extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B, int Co,
-                                   int Ci, long N, fno_stream_t stream) {
+// Wm / dx != nullptr: also write the data gradient dx = W^T ds when the TMA-fed kernel can carry it (returns 1 in
+// *fused then); otherwise only the weight gradient is computed and the caller runs the product separately.
+static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, float* gb, void* work, int B, int Co, int Ci,
+                                long N, const float* Wm, float* dx, int* fused, fno_stream_t stream) {
+  if (fused) *fused = 0;
   if (!ds || !a || !work || B <= 0 || Co <= 0 || Ci <= 0 || N <= 0) {
     set_error("fno_pointwise_wgrad: bad argument");
     return FNO_E_ARG;
@@ -517,8 +561,10 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
   if (aligned && smem2 <= 200 * 1024 && ntiles <= WG2_MAXW) {
     static std::atomic<int> attr2_done{0};
     if (!attr2_done.load()) {
-      if (cudaFuncSetAttribute(wgrad2_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-          cudaSuccess)
+      if (cudaFuncSetAttribute(wgrad2_partial_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+              cudaSuccess ||
+          cudaFuncSetAttribute(wgrad2_partial_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
+              cudaSuccess)
         return check_launch("cudaFuncSetAttribute(wgrad2)");
       attr2_done.store(1);
     }
@@ -529,8 +575,17 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
     long ctas2 = total2s < 148 ? total2s : 148;
     const long spc2 = (total2s + ctas2 - 1) / ctas2;
     ctas2 = (total2s + spc2 - 1) / spc2;
-    wgrad2_partial_kernel<T><<<dim3((unsigned)ctas2, 1), 32 * (warps2 + 1), smem2, st>>>(
-        ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH);
+    // the data gradient rides along when the 8 consumer warps cover a slab two pixels per thread
+    const size_t smem2d = smem2 + sizeof(float) * (size_t)Co * 2 * T;
+    const bool dgrad = Wm != nullptr && dx != nullptr && warps2 == WG2_MAXW && Co <= 2 * T && Ci <= 2 * T &&
+                       smem2d <= 200 * 1024 && (reinterpret_cast<size_t>(dx) % 8) == 0;
+    if (dgrad)
+      wgrad2_partial_kernel<T, true><<<dim3((unsigned)ctas2, 1), 32 * warps2, smem2d, st>>>(
+          ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH, Wm, dx);
+    else
+      wgrad2_partial_kernel<T, false><<<dim3((unsigned)ctas2, 1), 32 * warps2, smem2, st>>>(
+          ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH, nullptr, nullptr);
+    if (dgrad && fused) *fused = 1;
     count_launch();
     int rc2 = check_launch("wgrad2_partial_kernel");
     if (rc2 != FNO_OK) return rc2;
@@ -548,4 +603,18 @@ extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, f
   wgrad_reduce_kernel<<<(total * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas, Co, Ci);
   count_launch();
   return check_launch("wgrad_reduce_kernel");
+}
+
+extern "C" int fno_pointwise_wgrad(const float* ds, const float* a, float* gW, float* gb, void* work, int B, int Co,
+                                   int Ci, long N, fno_stream_t stream) {
+  return pointwise_wgrad_impl(ds, a, gW, gb, work, B, Co, Ci, N, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int fno_pointwise_bwd(const float* ds, const float* a, const float* W, float* dx, float* gW, float* gb,
+                                 void* work, int B, int Co, int Ci, long N, fno_stream_t stream) {
+  if (!W || !dx) { set_error("fno_pointwise_bwd: bad argument"); return FNO_E_ARG; }
+  int fused = 0;
+  int rc = pointwise_wgrad_impl(ds, a, gW, gb, work, B, Co, Ci, N, W, dx, &fused, stream);
+  if (rc != FNO_OK || fused) return rc;
+  return fno_pointwise_fwd(ds, W, nullptr, dx, B, Co, Ci, N, /*transpose=*/1, stream);
 }

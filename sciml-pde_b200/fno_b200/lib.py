@@ -69,6 +69,7 @@ def load():
             "fno_pointwise_fwd": (i, [vp, vp, vp, vp, i, i, i, l, i, vp]),
             "fno_pointwise_wgrad_workspace_bytes": (C.c_size_t, [i, i, i, l]),
             "fno_pointwise_wgrad": (i, [vp, vp, vp, vp, vp, i, i, i, l, vp]),
+            "fno_pointwise_bwd": (i, [vp, vp, vp, vp, vp, vp, vp, i, i, i, l, vp]),
             "fno_lift_stats_workspace_bytes": (C.c_size_t, [i, i]),
             "fno_lift_stats": (i, [vp, vp, vp, i, l, i, vp]),
             "fno_lift_fwd": (i, [vp, vp, vp, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp]),
@@ -105,7 +106,7 @@ EXPORTED_SYMBOLS = (
     "fno_sc2d_fwd_transform", "fno_sc2d_fwd_workspace_bytes", "fno_sc2d_fwd_transform_ws",
     "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
-    "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad",
+    "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad", "fno_pointwise_bwd",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
     "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
@@ -344,6 +345,21 @@ def pointwise_wgrad_buffers(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, 
     gw = torch.empty(tuple(weight_shape), dtype=torch.float32, device=ds.device)
     gb = torch.empty(Co, dtype=torch.float32, device=ds.device) if need_bias else None
     return gw, gb, work
+
+
+def pointwise_bwd(ds: torch.Tensor, a: torch.Tensor, weight: torch.Tensor, *, need_bias: bool = True):
+    """Autograd of the 1x1 convolution in one call: (dx = W^T ds, gW, gb).  ds is read once when the TMA-fed
+    weight-gradient kernel can carry the data gradient (fno_pointwise_bwd)."""
+    for t, n in ((ds, "ds"), (a, "a"), (weight, "weight")):
+        _require(t, torch.float32, n)
+    gw, gb, work = pointwise_wgrad_buffers(ds, a, weight.shape, need_bias=need_bias)
+    B, Co, Ci = ds.shape[0], ds.shape[1], a.shape[1]
+    N = ds.numel() // (B * Co)
+    dx = torch.empty_like(a)
+    rc = load().fno_pointwise_bwd(ds.data_ptr(), a.data_ptr(), weight.data_ptr(), dx.data_ptr(), gw.data_ptr(), _ptr(gb),
+                                  work.data_ptr(), B, Co, Ci, N, _stream())
+    _check(rc, "fno_pointwise_bwd")
+    return dx, gw, gb
 
 
 def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True, buffers=None):

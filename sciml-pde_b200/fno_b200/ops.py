@@ -135,7 +135,11 @@ class FourierLayerFn(torch.autograd.Function):
             gY = lib.fwd_transform(plan, g, cmode=1, scale=inv_n)
         gwl = gbl = None
         forked = False
-        if need_wl or (need_bl and ctx.has_bias):
+        ga_lin = None
+        if need_ga and need_wl and not OVERLAP:
+            # weight, bias and data gradient of the bypass in one pass over ds (fno_pointwise_bwd)
+            ga_lin, gwl, gbl = lib.pointwise_bwd(ds, a, wl, need_bias=ctx.has_bias)
+        elif need_wl or (need_bl and ctx.has_bias):
             if OVERLAP:
                 main, side = torch.cuda.current_stream(), _side_stream(g.device)
                 bufs = lib.pointwise_wgrad_buffers(ds, a, wl.shape, need_bias=ctx.has_bias)
@@ -148,7 +152,7 @@ class FourierLayerFn(torch.autograd.Function):
         gX, gws = lib.mix_bwd(plan, X, gY, weights, need_gx=need_ga, need_gw=need_gw)
         ga = None
         if need_ga:
-            ga = lib.pointwise_fwd(ds, wl, None, transpose=True)
+            ga = ga_lin if ga_lin is not None else lib.pointwise_fwd(ds, wl, None, transpose=True)
             lib.inv_transform(plan, gX, addend=ga, out=ga, cmode=0, scale=1.0)
         if forked:
             main.wait_stream(side)

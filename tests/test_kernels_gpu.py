@@ -180,6 +180,11 @@ def test_pointwise_fwd_transpose_wgrad(lib, B, Co, Ci, spatial):
     a2 = a.reshape(B, Ci, -1).astype(np.float64)
     assert O.rel_err(gw.cpu().numpy().reshape(Co, Ci), np.einsum("bop,bip->oi", ds2, a2)) < TOL
     assert O.rel_err(gb.cpu().numpy(), ds2.sum(axis=(0, 2))) < TOL
+    # fused autograd (fno_pointwise_bwd): data, weight and bias gradient in one pass over ds when eligible
+    dx, gw3, gb3 = lib.pointwise_bwd(dev(ds), dev(a), dev(w))
+    assert O.rel_err(dx.cpu().numpy(), np.einsum("oi,bo...->bi...", w2, ds.astype(np.float64))) < TOL
+    assert O.rel_err(gw3.cpu().numpy().reshape(Co, Ci), np.einsum("bop,bip->oi", ds2, a2)) < TOL
+    assert O.rel_err(gb3.cpu().numpy(), ds2.sum(axis=(0, 2))) < TOL
 
 
 def test_transform_properties_full_size(lib):
