@@ -99,6 +99,14 @@ __device__ __forceinline__ void tmem_st16(unsigned taddr, const float (&v)[16]) 
         "r"(__float_as_uint(v[15]))
       : "memory");
 }
+// 8 registers -> 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 16 / 8 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {

@@ -357,6 +357,8 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
 //   T1[h] = Tc - i Ts;  with A^c_j = sum_h Tc cos(j th), B^c_j = sum_h Tc sin(j th) (same for Ts)
 //   X[+j, k2] = (A^c - B^s) - i (B^c + A^s),   X[-j, k2] = (A^c + B^s) + i (B^c - A^s)
 // ------------------------------------------------------------------------------------------
+constexpr int HP_S = 4;   // row slices per (plane, k2): adjacent lanes, combined with two shuffle steps
+
 template <int M1T>
 __global__ void __launch_bounds__(256)
 hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float* __restrict__ twH, int H, int W,
@@ -373,12 +375,15 @@ hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float
     for (int i = tid; i < NP * JP / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
   }
   __syncthreads();
-  const int g = tid / m2;
-  const int k2 = tid - g * m2;
+  // thread = (plane g, wavenumber k2, row slice sl); the HP_S slices of one (g, k2) are adjacent lanes of a warp
+  // (blockDim is a multiple of 32 and HP_S divides 32), idle threads of the last warp keep running for the shuffles
+  const int sl = tid & (HP_S - 1);
+  const int k2r = (tid / HP_S) % m2;
+  const int g = tid / (HP_S * m2);
   const long plane = (long)blockIdx.x * G + g;
-  if (g >= G || plane >= planes) return;
+  const bool live = g < G && plane < planes;
   const int TQ = (2 * m2 + 3) & ~3;          // row pitch of T1 (transform2d_tc.cu)
-  const float* __restrict__ tp = T1 + (size_t)plane * H * TQ + k2;
+  const float* __restrict__ tp = T1 + (size_t)(live ? plane : 0) * H * TQ + k2r;
   auto ld = [&](int h) -> Vec<2> {
     Vec<2> v;
     v.v[0] = __ldg(tp + (size_t)h * TQ);
@@ -390,30 +395,44 @@ hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float
   for (int n = 0; n < 2; ++n)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[n][j] = 0.0f;
-  fold_accumulate_even<M1T, 2>(acc, twH_s, ld(0));
-  const int npairs = (H - 1) / 2;
-  constexpr int PG = 4;
-  int t = 1;
-  for (; t + PG - 1 <= npairs; t += PG) {
-    Vec<2> v1[PG], v2[PG];
+  if (live) {
+    if (sl == 0) fold_accumulate_even<M1T, 2>(acc, twH_s, ld(0));
+    const int npairs = (H - 1) / 2;
+    constexpr int PG = 4;
+    int t = 1 + sl;                            // this slice's row pairs: 1 + sl, 1 + sl + HP_S, ...
+    for (; t + (PG - 1) * HP_S <= npairs; t += PG * HP_S) {
+      Vec<2> v1[PG], v2[PG];
 #pragma unroll
-    for (int u = 0; u < PG; ++u) { v1[u] = ld(t + u); v2[u] = ld(H - t - u); }
+      for (int u = 0; u < PG; ++u) { v1[u] = ld(t + u * HP_S); v2[u] = ld(H - t - u * HP_S); }
 #pragma unroll
-    for (int u = 0; u < PG; ++u) {
+      for (int u = 0; u < PG; ++u) {
+        Vec<2> e, o;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) { e.v[n] = v1[u].v[n] + v2[u].v[n]; o.v[n] = v1[u].v[n] - v2[u].v[n]; }
+        fold_accumulate<M1T, 2>(acc, twH_s + (t + u * HP_S) * JP, e, o);
+      }
+    }
+    for (; t <= npairs; t += HP_S) {
+      const Vec<2> a = ld(t), b = ld(H - t);
       Vec<2> e, o;
 #pragma unroll
-      for (int n = 0; n < 2; ++n) { e.v[n] = v1[u].v[n] + v2[u].v[n]; o.v[n] = v1[u].v[n] - v2[u].v[n]; }
-      fold_accumulate<M1T, 2>(acc, twH_s + (t + u) * JP, e, o);
+      for (int n = 0; n < 2; ++n) { e.v[n] = a.v[n] + b.v[n]; o.v[n] = a.v[n] - b.v[n]; }
+      fold_accumulate<M1T, 2>(acc, twH_s + t * JP, e, o);
     }
+    if ((H & 1) == 0 && sl == HP_S - 1) fold_accumulate_even<M1T, 2>(acc, twH_s + (H / 2) * JP, ld(H / 2));
   }
-  for (; t <= npairs; ++t) {
-    const Vec<2> a = ld(t), b = ld(H - t);
-    Vec<2> e, o;
+  // combine the row slices (adjacent lanes)
 #pragma unroll
-    for (int n = 0; n < 2; ++n) { e.v[n] = a.v[n] + b.v[n]; o.v[n] = a.v[n] - b.v[n]; }
-    fold_accumulate<M1T, 2>(acc, twH_s + t * JP, e, o);
-  }
-  if ((H & 1) == 0) fold_accumulate_even<M1T, 2>(acc, twH_s + (H / 2) * JP, ld(H / 2));
+  for (int n = 0; n < 2; ++n)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      float v = acc[n][j];
+#pragma unroll
+      for (int off = 1; off < HP_S; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc[n][j] = v;
+    }
+  if (!live || sl != 0) return;
+  const int k2 = k2r;
   float sc = scale;
   if (cmode && k2 != 0 && !((W & 1) == 0 && 2 * k2 == W)) sc *= 2.0f;
   float2* Xp = X + (size_t)plane * (2 * m1) * m2;
@@ -1110,9 +1129,10 @@ int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_o
 
 template <int M1T>
 static int launch_hpass_t(const Plan* p, const float* T1, float* X, long planes, int cmode, float scale, cudaStream_t st) {
-  int G = 256 / p->m2;
-  if (G > 8) G = 8;                                   // ~100-thread CTAs: enough CTAs to cover 148 SMs
-  const int threads = round_threads(G * p->m2);
+  int G = 256 / (p->m2 * HP_S);
+  if (G > 2) G = 2;                                   // ~100-thread CTAs, > 1000 of them at a bench-sized batch
+  if (G < 1) { set_error("hpass2d: modes2 %d too large", p->m2); return FNO_E_ARG; }
+  const int threads = round_threads(G * p->m2 * HP_S);
   const size_t smem = sizeof(float) * (size_t)p->NP * p->JP;
   const unsigned grid = (unsigned)((planes + G - 1) / G);
   hpass2d_kernel<M1T><<<grid, threads, smem, st>>>(T1, reinterpret_cast<float2*>(X), p->twH, p->H, p->W, p->m1, p->m2, G,
@@ -1123,8 +1143,7 @@ static int launch_hpass_t(const Plan* p, const float* T1, float* X, long planes,
 
 // K1 with a caller-provided workspace: W-axis stage on the tensor cores + H-axis fold on the FP32 pipes
 // when the geometry allows (even W <= 136, 2*m2 <= 32) and the batch is large enough to fill the
-// persistent grid; otherwise the direct kernel.  The caller opts in by passing the workspace: at
-// width 20 / fp32 mode the direct kernel is faster (137 vs 101 us at cfg 1).
+// persistent grid; otherwise the direct kernel.
 int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, float* work,
                     long planes, int cmode, float scale, cudaStream_t st) {
   const bool aligned = ((reinterpret_cast<size_t>(x) | reinterpret_cast<size_t>(preact) | reinterpret_cast<size_t>(ds_out)) & 7) == 0 &&
@@ -1132,7 +1151,15 @@ int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* d
   if (work == nullptr || p->tc_nch == 0 || !aligned || planes * p->H < 4096 ||
       sizeof(float) * (size_t)p->NP * p->JP > 48 * 1024)
     return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
-  int rc = launch_fwd2d_tc(p, x, preact, ds_out, work, planes, st, false);
+  // plain transform: A operand through TMEM (v2, 44 + 22 us against 100 us for the FP32 kernel at cfg 1).  With
+  // the GELU' premultiply the FP32 kernel stays (174 us; the shared-memory staged v1 measured 262 us and is kept
+  // behind FNO_K1_TC_V1=1 for reference).
+  static const bool v1 = [] { const char* e = std::getenv("FNO_K1_TC_V1"); return e != nullptr && e[0] == '1'; }();
+  int rc = (preact == nullptr && !v1) ? launch_fwd2d_tca(p, x, work, planes, st, false) : 1;
+  if (rc == 1) {
+    if (!v1) return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
+    rc = launch_fwd2d_tc(p, x, preact, ds_out, work, planes, st, false);
+  }
   if (rc != FNO_OK) return rc;
   switch (p->M1T) {
     case 4: return launch_hpass_t<4>(p, work, X, planes, cmode, scale, st);

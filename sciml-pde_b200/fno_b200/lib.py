@@ -95,9 +95,9 @@ def load():
     return _lib
 
 
-# K1 with its contiguous-axis half as a tcgen05 truncated-DFT GEMM (transform2d_tc.cu).  Opt-in: at
-# width 20 in fp32 mode (3xTF32) the direct FP32 kernel is faster.
-K1_TENSOR_CORES = os.environ.get("FNO_K1_TC", "0") == "1"
+# K1 with its contiguous-axis half as a tcgen05 truncated-DFT GEMM (transform2d_tc.cu, A operand through
+# TMEM, 3xTF32: fp32-mode accuracy) followed by the FP32 strided-axis fold.  FNO_K1_TC=0 selects the all-FP32 kernel.
+K1_TENSOR_CORES = os.environ.get("FNO_K1_TC", "1") != "0"
 
 EXPORTED_SYMBOLS = (
     "fno_version", "fno_sm_arch", "fno_last_error", "fno_launch_count", "fno_shutdown",
