@@ -62,7 +62,7 @@ constexpr unsigned TM_D2 = 256;      // 2 slots x 32: dh tile
 constexpr unsigned TM_D3 = 320;      // 32: gW1 | gb1, accumulated over the CTA's lifetime
 constexpr unsigned TM_COLS = 512;
 
-// per-CTA partial record (floats): gW1|gb1 [128][32], gW2 [4 quarters][4][128], gb2 [64 px][4]
+// per-CTA partial record (floats): gW1|gb1 [128][32], gW2 [4 quarters][4][128], gb2 [2 warps][4] (padded to 64 x 4)
 constexpr int REC_W1 = 0, REC_W2 = BT_HID * BT_NC, REC_B2 = REC_W2 + 4 * BT_GV * BT_HID;
 constexpr int REC_LEN = REC_B2 + BT_PX * BT_GV;
 
@@ -461,9 +461,14 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       }
       load_raw(ra, it + 4);
     }
-    if (kq == 0) {
+    if (kq == 0) {                                  // gb2: the two dout-staging warps reduce over their 32 pixels each
 #pragma unroll
-      for (int v = 0; v < BT_GV; ++v) myrec[REC_B2 + px * BT_GV + v] = gb2[v];
+      for (int v = 0; v < BT_GV; ++v) {
+        float t = gb2[v];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) myrec[REC_B2 + lw * BT_GV + v] = t;
+      }
     }
   }
   tc_fence_before();
@@ -485,7 +490,7 @@ head_bwd_tc_reduce_kernel(const float* __restrict__ rec, int nrec, float* __rest
   if (idx < n1) { const int j = idx / C, c = idx - j * C; base = REC_W1 + j * BT_NC + c; inner = 1; istride = 0; dst = gW1 + idx; }
   else if (idx < n2) { const int j = idx - n1; base = REC_W1 + j * BT_NC + C; inner = 1; istride = 0; dst = gb1 + j; }
   else if (idx < n3) { const int k = idx - n2, v = k / BT_HID, j = k - v * BT_HID; base = REC_W2 + v * BT_HID + j; inner = 4; istride = BT_GV * BT_HID; dst = gW2 + k; }
-  else { const int v = idx - n3; base = REC_B2 + v; inner = BT_PX; istride = BT_GV; dst = gb2 + v; }
+  else { const int v = idx - n3; base = REC_B2 + v; inner = 2; istride = BT_GV; dst = gb2 + v; }
   float s = 0.f;
   const int total = nrec * inner;
   for (int t = lane; t < total; t += 32) {

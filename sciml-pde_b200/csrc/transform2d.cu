@@ -360,7 +360,7 @@ fwd2d_kernel(const float* __restrict__ x, const float* __restrict__ preact, floa
 constexpr int HP_S = 4;   // row slices per (plane, k2): adjacent lanes, combined with two shuffle steps
 
 template <int M1T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(384)
 hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float* __restrict__ twH, int H, int W,
                int m1, int m2, int G, long planes, int cmode, float scale) {
   constexpr int NJ = Geo<M1T>::NJ;
@@ -1129,8 +1129,9 @@ int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_o
 
 template <int M1T>
 static int launch_hpass_t(const Plan* p, const float* T1, float* X, long planes, int cmode, float scale, cudaStream_t st) {
-  int G = 256 / (p->m2 * HP_S);
-  if (G > 2) G = 2;                                   // ~100-thread CTAs, > 1000 of them at a bench-sized batch
+  int G = 384 / (p->m2 * HP_S);
+  if (G > 2) G = 2;                                   // ~100-thread CTAs, > 1000 of them at a bench-sized batch (measured:
+                                                      // 8 planes per CTA, which amortises the 7 KB twiddle table, is slower)
   if (G < 1) { set_error("hpass2d: modes2 %d too large", p->m2); return FNO_E_ARG; }
   const int threads = round_threads(G * p->m2 * HP_S);
   const size_t smem = sizeof(float) * (size_t)p->NP * p->JP;
