@@ -55,6 +55,7 @@ constexpr int TCF_EPI_THREADS = 32 * TCF_EPI_WARPS;
 constexpr int TCF_THREADS = TCF_EPI_THREADS + 32;
 constexpr int TCF_MAXCH = 2;               // 16-byte channel chunks staged per thread (K <= 32 channels)
 
+template <int NV>   // output variables accumulated per hidden unit: 2 (V <= 2) or 4
 __global__ void __launch_bounds__(TCF_THREADS, 1)
 head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
                    const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
@@ -204,9 +205,14 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           const float gl = gelu_fast(v[i] + b1s[j0 + i]);
-          const float4 w = *reinterpret_cast<const float4*>(W2s + (j0 + i) * TC_VP);
-          o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
-          o[2] = fmaf(w.z, gl, o[2]); o[3] = fmaf(w.w, gl, o[3]);
+          if (NV == 2) {
+            const float2 w = *reinterpret_cast<const float2*>(W2s + (j0 + i) * TC_VP);
+            o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
+          } else {
+            const float4 w = *reinterpret_cast<const float4*>(W2s + (j0 + i) * TC_VP);
+            o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
+            o[2] = fmaf(w.z, gl, o[2]); o[3] = fmaf(w.w, gl, o[3]);
+          }
         }
       }
       // combine the four column quarters through shared memory (double-buffered: one barrier per
@@ -267,13 +273,17 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
                       6 * sizeof(unsigned long long) + 16;
   static std::atomic<int> done{0};
   if (!done.load()) {
-    if (cudaFuncSetAttribute(head_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(head_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(head_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_fwd_tc)");
     done.store(1);
   }
   const int ctas = (int)(total < 148 ? total : 148);
-  head_fwd_tc_kernel<<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total,
-                                                      g_math_mode.load() == FNO_MATH_TF32);
+  const int single = g_math_mode.load() == FNO_MATH_TF32;
+  if (V <= 2)
+    head_fwd_tc_kernel<2><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
+  else
+    head_fwd_tc_kernel<4><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
   count_launch();
   return check_launch("head_fwd_tc_kernel");
 }
