@@ -52,6 +52,8 @@ int setup_transform2d_attrs(const Plan* p);
 int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, float* work,
                     long planes, int cmode, float scale, cudaStream_t st);
 size_t fwd2d_tc_smem_bytes(int nch);
+int launch_fwd2d_tcap(const Plan* p, const float* g, const float* preact, float* ds_out, float* T1, long planes,
+                      cudaStream_t st, bool attr_only);
 int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cudaStream_t st, bool attr_only);
 int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
                     cudaStream_t st, bool attr_only);

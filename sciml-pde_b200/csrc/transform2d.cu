@@ -1156,7 +1156,10 @@ int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* d
   // the GELU' premultiply the FP32 kernel stays (174 us; the shared-memory staged v1 measured 262 us and is kept
   // behind FNO_K1_TC_V1=1 for reference).
   static const bool v1 = [] { const char* e = std::getenv("FNO_K1_TC_V1"); return e != nullptr && e[0] == '1'; }();
-  int rc = (preact == nullptr && !v1) ? launch_fwd2d_tca(p, x, work, planes, st, false) : 1;
+  static const bool premul_tc = [] { const char* e = std::getenv("FNO_K1P_TC"); return e == nullptr || e[0] != '0'; }();
+  int rc = 1;
+  if (!v1) rc = (preact == nullptr) ? launch_fwd2d_tca(p, x, work, planes, st, false)
+                                    : (premul_tc ? launch_fwd2d_tcap(p, x, preact, ds_out, work, planes, st, false) : 1);
   if (rc == 1) {
     if (!v1) return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
     rc = launch_fwd2d_tc(p, x, preact, ds_out, work, planes, st, false);
