@@ -193,9 +193,9 @@ fwd2d_tc_kernel(const float* __restrict__ x, const float* __restrict__ preact, f
 // ~4 instructions.  A is written in two K halves so that the MMAs of one half run under the conversion of
 // the other; the accumulator is double-buffered for the epilogue (T1 rows to global, 16-byte stores).
 // ------------------------------------------------------------------------------------------
-constexpr int TA_CONV_WARPS = 8;           // 4 lane quadrants x 2 K halves
-constexpr int TA_MMA_WARP = 8, TA_LOAD_WARP = 9, TA_EPI_WARP0 = 10;
-constexpr int TA_THREADS = 32 * 14;
+constexpr int TA_CONV_WARPS = 16;          // 4 lane quadrants x 4 K quarters (two quarters per K half)
+constexpr int TA_MMA_WARP = 16, TA_LOAD_WARP = 17, TA_EPI_WARP0 = 18;
+constexpr int TA_THREADS = 32 * 22;
 constexpr int TA_MAXK = 136;               // K padding limit: 17 k-steps; A hi | lo = 272 TMEM columns
 constexpr unsigned TA_TM_LO = TA_MAXK;     // column of the lo half of A
 constexpr unsigned TA_TM_D = 288;          // 2 x 32 accumulator columns
@@ -261,9 +261,10 @@ fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const floa
     }
   } else if (warp < TA_CONV_WARPS) {
     // ---- converters: thread = row (TMEM lane), one K half ------------------------------------------
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, kq = warp >> 2, half = kq >> 1;
     const int row = quad * 32 + lane;
-    const int ks0 = half ? kh0 : 0, ks1 = half ? ksteps : kh0;
+    const int hs0 = half ? kh0 : 0, hs1 = half ? ksteps : kh0, hm = (hs0 + hs1 + 1) / 2;   // this half, split in two
+    const int ks0 = (kq & 1) ? hm : hs0, ks1 = (kq & 1) ? hs1 : hm;
     const unsigned ta = tmem_base + ((unsigned)(quad * 32) << 16);
     for (int it = 0; it < ntl; ++it) {
       const int s = it & 1;
@@ -443,10 +444,11 @@ fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact,
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp < TA_CONV_WARPS) {
     // ---- converters: thread = row (TMEM lane), one K half ------------------------------------------
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, kq = warp >> 2, half = kq >> 1;
     const int row = quad * 32 + lane;
     const int slot = quad >> 1, lrow = row - slot * HR;        // half-tile slot of this lane quadrant
-    const int ks0 = half ? kh0 : 0, ks1 = half ? ksteps : kh0;
+    const int hs0 = half ? kh0 : 0, hs1 = half ? ksteps : kh0, hm = (hs0 + hs1 + 1) / 2;   // this half, split in two
+    const int ks0 = (kq & 1) ? hm : hs0, ks1 = (kq & 1) ? hs1 : hm;
     const unsigned ta = tmem_base + ((unsigned)(quad * 32) << 16);
     for (int it = 0; it < ntl; ++it) {
       const long row0 = ((long)blockIdx.x + (long)it * gridDim.x) * TW_M;
