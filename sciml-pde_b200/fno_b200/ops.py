@@ -25,6 +25,7 @@ from . import lib
 # sees a cross-stream block; under CUDA-graph capture the fork/join become parallel graph branches.
 # ---------------------------------------------------------------------------------------------
 _side_streams: dict = {}
+OVERLAP_FWD = os.environ.get("FNO_OVERLAP_FWD", "0") == "1"   # bypass on a side stream next to K1 / K2 (forward only)
 OVERLAP = os.environ.get("FNO_OVERLAP", "0") == "1"   # measured: no gain at cfg 1 (5.877 vs 5.893 ms), the first kernel fills every SM
 
 
@@ -97,7 +98,7 @@ class FourierLayerFn(torch.autograd.Function):
         wl = wl.contiguous()
         plan = _plan_for(a, weights)
         training = any(ctx.needs_input_grad)
-        if OVERLAP:
+        if OVERLAP or OVERLAP_FWD:
             main, side = torch.cuda.current_stream(), _side_stream(a.device)
             lin = torch.empty((a.shape[0], wl.shape[0]) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
             side.wait_stream(main)
