@@ -125,7 +125,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -139,6 +139,13 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return None
+        if not self.lines:                      # nothing delivered yet: one synchronous query right after the timed region
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                self.lines.extend(ln.strip() for ln in out.splitlines() if ln.strip())
+            except Exception:
+                pass
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -312,12 +319,14 @@ def run_ours(args):
     l0 = lib.launch_count()
     eager_step(*devb[0])                      # also counts this library's launches per (eager) step
     launches_per_step = lib.launch_count() - l0
-    for i in range(max(W, 3)):                # graph mode: calls 1-2 eager, call 3 captures
-        step(*devb[i % 2])
-    barrier()
+    # the clock sampler starts before the warm-up steps (same load as the timed steps): nvidia-smi needs ~100 ms to
+    # deliver its first line and the timed region of a short run is shorter than that
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for i in range(max(W, 3)):                # graph mode: calls 1-2 eager, call 3 captures
+        step(*devb[i % 2])
+    barrier()
     l0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
