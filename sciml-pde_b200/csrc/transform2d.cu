@@ -775,27 +775,32 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
     }
   }
 
-  // stage B: H-axis pass, two rows per step, fused epilogue
+  // stage B: H-axis pass, two rows per step, fused epilogue.  Rows are addressed by ELEMENT OFFSETS that are
+  // multiples of W kept in 32-bit registers (one IMAD per row shared by the three arrays); the per-access
+  // 64-bit `base + h * W` rebuild cost five integer instructions per load / store (ncu r1_e: LEA + IADD3 + MOV
+  // were 27 % of this kernel's instructions, which is FP32-issue-bound).
   const size_t base = (size_t)plane * H * W + w0;
   const bool has_add = addend != nullptr;
   const float* ap = has_add ? addend + base : nullptr;
   float* __restrict__ sop = s_out != nullptr ? s_out + base : nullptr;
   float* op = out + base;
-  auto ld_add = [&](int h) -> Vec<TN> {
-    if (has_add) return Vec<TN>::ld_plain(ap + h * W);
+  auto ld_add_o = [&](unsigned off) -> Vec<TN> {
+    if (has_add) return Vec<TN>::ld_plain(ap + off);
     Vec<TN> z;
 #pragma unroll
     for (int n = 0; n < TN; ++n) z.v[n] = 0.f;
     return z;
   };
-  auto emit = [&](int h, Vec<TN> v) {
-    if (sop != nullptr) v.st(sop + h * W);
+  auto ld_add = [&](int h) -> Vec<TN> { return ld_add_o((unsigned)h * (unsigned)W); };
+  auto emit_o = [&](unsigned off, Vec<TN> v) {
+    if (sop != nullptr) v.st(sop + off);
     if (apply_gelu) {
 #pragma unroll
       for (int n = 0; n < TN; ++n) v.v[n] = gelu_fast(v.v[n]);
     }
-    v.st(op + h * W);
+    v.st(op + off);
   };
+  auto emit = [&](int h, Vec<TN> v) { emit_o((unsigned)h * (unsigned)W, v); };
   auto eval = [&](int t, Vec<TN>& e, Vec<TN>& o) {
     float tw[JP];
     load_row<JP>(tw, twH_s + (size_t)t * JP);
@@ -828,24 +833,26 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
   // any of the group's stores, and the next group's loads before this group's arithmetic.
   constexpr int PG = (TN == 2) ? 2 : 4;
   int t = 1;
+  const unsigned uW = (unsigned)W;
+  unsigned ou = uW, od = (unsigned)(H - 1) * uW;      // element offsets of rows t and H - t
   Vec<TN> a1[PG], a2[PG];
   if (t + PG - 1 <= npairs) {
 #pragma unroll
-    for (int u = 0; u < PG; ++u) { a1[u] = ld_add(t + u); a2[u] = ld_add(H - t - u); }
+    for (int u = 0; u < PG; ++u) { a1[u] = ld_add_o(ou + u * uW); a2[u] = ld_add_o(od - u * uW); }
   }
-  for (; t + PG - 1 <= npairs; t += PG) {
+  for (; t + PG - 1 <= npairs; t += PG, ou += PG * uW, od -= PG * uW) {
     Vec<TN> n1[PG], n2[PG];
     const bool more = (t + 2 * PG - 1 <= npairs);
     if (has_add && t + PF_DIST + PG - 1 <= npairs) {
 #pragma unroll
       for (int u = 0; u < PG; ++u) {
-        prefetch_l2(ap + (t + PF_DIST + u) * W);
-        prefetch_l2(ap + (H - t - PF_DIST - u) * W);
+        prefetch_l2(ap + (ou + (PF_DIST + u) * uW));
+        prefetch_l2(ap + (od - (PF_DIST + u) * uW));
       }
     }
 #pragma unroll
     for (int u = 0; u < PG; ++u) {
-      if (more) { n1[u] = ld_add(t + PG + u); n2[u] = ld_add(H - t - PG - u); }
+      if (more) { n1[u] = ld_add_o(ou + (PG + u) * uW); n2[u] = ld_add_o(od - (PG + u) * uW); }
       else { n1[u] = a1[u]; n2[u] = a2[u]; }
     }
 #pragma unroll
@@ -857,8 +864,8 @@ inv2d_kernel(const float2* __restrict__ Y, const float* addend, float* __restric
         up.v[n] = e.v[n] + o.v[n] + a1[u].v[n];
         dn.v[n] = e.v[n] - o.v[n] + a2[u].v[n];
       }
-      emit(t + u, up);
-      emit(H - t - u, dn);
+      emit_o(ou + u * uW, up);
+      emit_o(od - u * uW, dn);
     }
 #pragma unroll
     for (int u = 0; u < PG; ++u) { a1[u] = n1[u]; a2[u] = n2[u]; }
