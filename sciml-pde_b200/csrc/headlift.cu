@@ -327,15 +327,20 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
   const int FR = (F + 1 + 3) & ~3, FQ = FR / 4;
   const int CQ = (C + 3) / 4, CR = 4 * CQ;
   const int nitems = CQ * FQ;
-  float* feat = sm;                           // [TILE][FR]
-  float* dhs = feat + TILE * FR;              // [CR][TP]: channel rows (pad rows zero)
+  // two tile buffers: tile i+1 is stored while tile i is multiplied -> ONE barrier per tile
+  const int buf_floats = TILE * FR + CR * TP;
+  float* feat0 = sm;                          // [2][ [TILE][FR] | [CR][TP] channel rows (pad rows zero) ]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // constant columns: bias feature = 1, padding = 0
-  for (int i = tid; i < TILE * (FR - F); i += LB2_THREADS) {
-    const int px = i / (FR - F), q = i - px * (FR - F);
-    feat[px * FR + F + q] = (q == 0) ? 1.f : 0.f;
+  for (int bsel = 0; bsel < 2; ++bsel) {
+    float* feat = feat0 + bsel * buf_floats;
+    float* dhs = feat + TILE * FR;
+    for (int i = tid; i < TILE * (FR - F); i += LB2_THREADS) {
+      const int px = i / (FR - F), q = i - px * (FR - F);
+      feat[px * FR + F + q] = (q == 0) ? 1.f : 0.f;
+    }
+    for (int i = tid; i < TP * (CR - C); i += LB2_THREADS) dhs[C * TP + i] = 0.f;
   }
-  for (int i = tid; i < TP * (CR - C); i += LB2_THREADS) dhs[C * TP + i] = 0.f;
   int cq[NIT], fq[NIT];
   float acc[NIT][4][4];
 #pragma unroll
@@ -396,12 +401,12 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
       dr[u] = v;
     }
   };
-  if ((int)blockIdx.x < tm.total) prefetch(blockIdx.x);
-
-  for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x) {
+  // registers -> tile buffer `bsel` (normalising x on the way); uses the sample / valid count of the prefetched tile
+  auto store_tile = [&](int bsel) {
+    float* feat = feat0 + bsel * buf_floats;
+    float* dhs = feat + TILE * FR;
     const float* __restrict__ mean = stats + (size_t)pb * 2 * V;
     const float* __restrict__ sd = mean + V;
-    __syncthreads();                          // the previous tile's products are done
 #pragma unroll
     for (int u = 0; u < XR; ++u) {
       if (xpx[u] < TILE) {
@@ -424,8 +429,23 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
       const int c = warp + u * (LB2_THREADS / 32);
       if (c < C) *reinterpret_cast<float2*>(dhs + c * TP + 2 * lane) = dr[u];
     }
-    __syncthreads();
-    if (tile + (int)gridDim.x < tm.total) prefetch(tile + gridDim.x);
+  };
+  int bsel = 0;
+  if ((int)blockIdx.x < tm.total) {
+    prefetch(blockIdx.x);
+    store_tile(0);
+    if ((int)(blockIdx.x + gridDim.x) < tm.total) prefetch(blockIdx.x + gridDim.x);
+  }
+  __syncthreads();
+
+  for (int tile = blockIdx.x; tile < tm.total; tile += gridDim.x) {
+    // the registers hold tile + gridDim.x: store it into the other buffer, then put tile + 2 gridDim.x in flight
+    if (tile + (int)gridDim.x < tm.total) {
+      store_tile(bsel ^ 1);
+      if (tile + 2 * (int)gridDim.x < tm.total) prefetch(tile + 2 * gridDim.x);
+    }
+    const float* feat = feat0 + bsel * buf_floats;
+    const float* dhs = feat + TILE * FR;
 #pragma unroll
     for (int j = 0; j < LB2_SLICE; ++j) {
       const int px = warp * LB2_SLICE + j;
@@ -440,6 +460,8 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
           for (int bb = 0; bb < 4; ++bb) acc[k][a][bb] = fmaf(dv[a], fv[bb], acc[k][a][bb]);
       }
     }
+    __syncthreads();                          // tile done by every warp; the other buffer is complete
+    bsel ^= 1;
   }
   // combine the eight pixel slices, then one partial record per CTA: part[cta][c][F + 1]
   __syncthreads();
@@ -997,7 +1019,7 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
     const bool aligned = (reinterpret_cast<size_t>(x) & 15) == 0;
     if ((T * V) % 4 == 0 && aligned && NIT <= 2 && C * (TILE / 2) <= 3 * LB2_THREADS && TILE * (T * V / 4) <= 2 * LB2_THREADS && TILE * G <= LB2_THREADS &&
         Wp % 2 == 0 && (reinterpret_cast<size_t>(dh) & 7) == 0) {
-      const size_t tile_bytes = sizeof(float) * ((size_t)TILE * FQ * 4 + (size_t)CQ * 4 * TP);
+      const size_t tile_bytes = 2 * sizeof(float) * ((size_t)TILE * FQ * 4 + (size_t)CQ * 4 * TP);   // double-buffered
       const size_t red_bytes = sizeof(float) * (size_t)(LB2_THREADS / 32) * nitems * 16;
       const size_t smem2 = tile_bytes > red_bytes ? tile_bytes : red_bytes;
       const int ctas = tm0.total < LB_CTAS ? tm0.total : LB_CTAS;
