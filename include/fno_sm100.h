@@ -52,9 +52,9 @@ void fno_shutdown(void);                       /* destroys every live plan */
 /* Arithmetic mode of the tensor-core kernels (process-wide, read at launch).  FNO_MATH_FP32 (default):
  * every tcgen05.mma operand is split hi + lo and three MMAs accumulate lo*hi + hi*lo + hi*hi ("3xTF32"):
  * results within the fp32-mode tolerance (<= 1e-5 relative).  FNO_MATH_TF32: a single kind::tf32 pass
- * (10-bit mantissa operands, fp32 accumulate); stated bound <= 2e-3 relative on the projection head's
- * outputs and gradients (tests/test_kernels_gpu.py::test_head_tf32_mode).  The FP32 CUDA-core kernels
- * are not affected.  Returns the previous mode, or a negative error code.                          */
+ * (10-bit mantissa operands, fp32 accumulate); stated bound <= 2e-3 relative on the outputs and gradients of
+ * the projection head and of the forward transform's truncated-DFT GEMM (tests/test_kernels_gpu.py::
+ * test_head_tf32_mode, ::test_fwd_transform_tf32_mode).  The FP32 CUDA-core kernels are not affected.  Returns the previous mode, or a negative error code.                          */
 #define FNO_MATH_FP32 0
 #define FNO_MATH_TF32 1
 int fno_set_math_mode(int mode);

@@ -203,7 +203,7 @@ constexpr unsigned TA_TM_COLS = 512;
 
 __global__ void __launch_bounds__(TA_THREADS, 1)
 fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const float* __restrict__ Fhi,
-                 const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles) {
+                 const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles, int single) {
   extern __shared__ __align__(128) unsigned char wsm[];
   const int raw_bytes = TW_M * W * 4;                 // one tile of rows (multiple of 512)
   const int f_bytes = 4 * nch * 128;
@@ -286,7 +286,7 @@ fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const floa
           split_tf32(v.y, hi[e + 1], lo[e + 1]);
         }
         tmem_st8(ta + (unsigned)(8 * ks), hi);
-        tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
+        if (!single) tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -313,9 +313,11 @@ fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const floa
         for (int ks = ks0; ks < ks1; ++ks) {
           const unsigned long long fo = (unsigned long long)(ks * (256 >> 4));
           const unsigned ah = tmem_base + (unsigned)(8 * ks), al = ah + TA_TM_LO;
-          tc_mma_tf32_ts_elect(td, al, d_fh + fo, idesc, ks != 0);     // lo * hi
-          tc_mma_tf32_ts_elect(td, ah, d_fl + fo, idesc, 1u);          // hi * lo
-          tc_mma_tf32_ts_elect(td, ah, d_fh + fo, idesc, 1u);          // hi * hi
+          if (!single) {                                               // tf32 mode: the hi * hi pass alone
+            tc_mma_tf32_ts_elect(td, al, d_fh + fo, idesc, ks != 0);   // lo * hi
+            tc_mma_tf32_ts_elect(td, ah, d_fl + fo, idesc, 1u);        // hi * lo
+          }
+          tc_mma_tf32_ts_elect(td, ah, d_fh + fo, idesc, single ? (unsigned)(ks != 0) : 1u);   // hi * hi
         }
         tc_commit_elect(a_free + half);
       }
@@ -357,7 +359,7 @@ fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const floa
 __global__ void __launch_bounds__(TA_THREADS, 1)
 fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact, float* __restrict__ ds_out,
                   float* __restrict__ T1, const float* __restrict__ Fhi,
-                 const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles) {
+                 const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles, int single) {
   extern __shared__ __align__(128) unsigned char wsm[];
   constexpr int HR = TW_M / 2;                        // rows per half-tile slot
   const int slot_bytes = HR * W * 4;                  // multiple of 256
@@ -475,7 +477,7 @@ fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact,
           split_tf32(v.y, hi[e + 1], lo[e + 1]);
         }
         tmem_st8(ta + (unsigned)(8 * ks), hi);
-        tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
+        if (!single) tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
       }
       tmem_st_wait();
       fence_proxy_async();                                     // dS writes -> visible to the bulk store
@@ -503,9 +505,11 @@ fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact,
         for (int ks = ks0; ks < ks1; ++ks) {
           const unsigned long long fo = (unsigned long long)(ks * (256 >> 4));
           const unsigned ah = tmem_base + (unsigned)(8 * ks), al = ah + TA_TM_LO;
-          tc_mma_tf32_ts_elect(td, al, d_fh + fo, idesc, ks != 0);     // lo * hi
-          tc_mma_tf32_ts_elect(td, ah, d_fl + fo, idesc, 1u);          // hi * lo
-          tc_mma_tf32_ts_elect(td, ah, d_fh + fo, idesc, 1u);          // hi * hi
+          if (!single) {                                               // tf32 mode: the hi * hi pass alone
+            tc_mma_tf32_ts_elect(td, al, d_fh + fo, idesc, ks != 0);   // lo * hi
+            tc_mma_tf32_ts_elect(td, ah, d_fl + fo, idesc, 1u);        // hi * lo
+          }
+          tc_mma_tf32_ts_elect(td, ah, d_fh + fo, idesc, single ? (unsigned)(ks != 0) : 1u);   // hi * hi
         }
         tc_commit_elect(a_free + half);
       }
@@ -585,7 +589,8 @@ int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cuda
     return 1;
   const int ctas = (int)(tiles < 148 ? tiles : 148);
   const int TQ = (2 * p->m2 + 3) & ~3;
-  fwd2d_tca_kernel<<<ctas, TA_THREADS, smem, st>>>(x, T1, p->tcF_hi, p->tcF_lo, R, p->W, p->tc_nch, TQ, (int)tiles);
+  fwd2d_tca_kernel<<<ctas, TA_THREADS, smem, st>>>(x, T1, p->tcF_hi, p->tcF_lo, R, p->W, p->tc_nch, TQ, (int)tiles,
+                                                   g_math_mode.load() == FNO_MATH_TF32);
   count_launch();
   return check_launch("fwd2d_tca_kernel");
 }
@@ -609,7 +614,7 @@ int launch_fwd2d_tcap(const Plan* p, const float* g, const float* preact, float*
   const int ctas = (int)(tiles < 148 ? tiles : 148);
   const int TQ = (2 * p->m2 + 3) & ~3;
   fwd2d_tcap_kernel<<<ctas, TA_THREADS, smem, st>>>(g, preact, ds_out, T1, p->tcF_hi, p->tcF_lo, R, p->W, p->tc_nch, TQ,
-                                                    (int)tiles);
+                                                    (int)tiles, g_math_mode.load() == FNO_MATH_TF32);
   count_launch();
   return check_launch("fwd2d_tcap_kernel");
 }

@@ -486,3 +486,32 @@ def test_device_windows_match_host_windows(lib, spatial, T, V, T0, R):
     # one epoch over two ranks covers every item exactly once
     seen = torch.cat([torch.cat(data.epoch_indices(len(ds), 8, True, 16, 0, r, 2)) for r in range(2)])
     assert sorted(seen.tolist()) == list(range(len(ds)))
+
+
+def test_fwd_transform_tf32_mode(lib, monkeypatch):
+    """tf32 math mode on the K1 tensor-core kernels (plain and GELU'-premultiply forms): single kind::tf32 pass,
+    stated bound <= 2e-3 relative; fp32 mode (3xTF32) <= 1e-5 on the same inputs."""
+    monkeypatch.setattr(lib, "K1_TENSOR_CORES", True)
+    B, C, H, W, m1, m2 = 4, 20, 130, 130, 12, 12
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    s_ = (rng.standard_normal((B, C, H, W)) * 1.5).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    ref_plain = O.fwd_transform(g, (m1, m2), cmode=0, scale=1.0)
+    ds_ref = g.astype(np.float64) * O.gelu_grad(s_.astype(np.float64))
+    ref_pre = O.fwd_transform(ds_ref, (m1, m2), cmode=1, scale=1.0 / (H * W))
+    errs = {}
+    for mode in ("tf32", "fp32"):
+        prev = lib.set_math_mode(mode)
+        try:
+            X = lib.fwd_transform(plan, dev(g), cmode=0, scale=1.0).cpu().numpy()
+            ds = torch.empty(B, C, H, W, device="cuda")
+            Xp = lib.fwd_transform(plan, dev(g), preact=dev(s_), ds_out=ds, cmode=1, scale=1.0 / (H * W)).cpu().numpy()
+        finally:
+            lib.set_math_mode(prev)
+        errs[mode] = (O.rel_err(X, ref_plain), O.rel_err(Xp, ref_pre), O.rel_err(ds.cpu().numpy(), ds_ref))
+    assert max(errs["fp32"]) < TOL, errs
+    assert max(errs["tf32"][:2]) < TF32_TOL, errs
+    assert errs["tf32"][2] < TOL                    # dS itself is computed in fp32 in both modes
+    assert errs["tf32"][0] > 10 * errs["fp32"][0], errs
+    print("K1 tf32-mode errors (plain, premultiply):", f"{errs['tf32'][0]:.2e}", f"{errs['tf32'][1]:.2e}")
