@@ -85,13 +85,17 @@ class FusedTrainStep:
     ``graph=True`` captures forward + loss + backward + update in ONE CUDA graph after two eager
     warm-up steps (the first discovers which parameters receive gradients); inputs are copied
     into static buffers, so a replay is a single launch -- at the reference's own batch sizes
-    (2-16) the eager step is bound by ~150 kernel launches, not by the GPU.  Under data
+    (2-16) the eager step is bound by ~150 kernel launches, not by the GPU.  With
+    ``alias_inputs=True`` the graph reads the caller's tensors in place instead (no 200 MB device copy
+    per step at batch 128): one graph is captured per distinct set of input addresses (up to
+    ``max_graphs``; a double-buffered input pipeline needs two), the caller keeps those tensors alive
+    and refills them between steps; other inputs fall back to the copying graph.  Under data
     parallelism (``dp``) the step stays eager: the bucket all-reduces are issued from autograd
     hooks and the optimizer reads the reduced bucket views in place (``own_grads=False``)."""
 
     def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-4, t_max: float = 0.0, betas=(0.9, 0.999),
                  eps: float = 1e-8, dp: Optional[BucketedGradAllReduce] = None, graph: bool = False,
-                 auxiliary_weight: Optional[float] = None):
+                 auxiliary_weight: Optional[float] = None, alias_inputs: bool = False, max_graphs: int = 2):
         from .steptail import FusedClipAdam
 
         self.model = model
@@ -104,6 +108,9 @@ class FusedTrainStep:
         self._graph = None
         self._static_in = None
         self._static_out = None
+        self.alias_inputs = alias_inputs
+        self.max_graphs = max_graphs
+        self._aliased = {}                      # input addresses -> (graph, inputs kept alive, static output)
 
     def _eager(self, *batch):
         from .steptail import nrmse_loss
@@ -150,6 +157,21 @@ class FusedTrainStep:
             with torch.cuda.graph(self._graph):
                 self._static_out = self._eager(*self._static_in)
             return ret
+        elif self.alias_inputs and all(t.is_contiguous() for t in batch):
+            key = tuple((t.data_ptr(), tuple(t.shape)) for t in batch)
+            hit = self._aliased.get(key)
+            if hit is None and len(self._aliased) < self.max_graphs:
+                # same parameters, optimizer state and step counter; only the input addresses differ.  Capture
+                # records, it does not execute: the replay below runs this batch's step.
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    out = self._eager(*batch)
+                hit = self._aliased[key] = (g, batch, out)
+            if hit is not None:
+                hit[0].replay()
+                return hit[2]
+            for dst, src in zip(self._static_in, batch):
+                dst.copy_(src, non_blocking=True)
         else:
             for dst, src in zip(self._static_in, batch):
                 dst.copy_(src, non_blocking=True)

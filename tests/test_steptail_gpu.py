@@ -76,7 +76,7 @@ def test_fused_clip_adam_vs_torch(scale):
     assert torch.equal(dead_our, dead_ref)
 
 
-@pytest.mark.parametrize("graph", [False, True])
+@pytest.mark.parametrize("graph", [False, True, "alias"])
 def test_fused_train_step_matches_torch_step(graph):
     from fno_b200 import data
     from fno_b200.fno import FNO2d
@@ -88,9 +88,12 @@ def test_fused_train_step_matches_torch_step(graph):
     opt = torch.optim.Adam(m_ref.parameters(), lr=1e-3, weight_decay=1e-4)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=50)
     ref_step = TrainStep(m_ref, opt, sched)
-    our_step = FusedTrainStep(m_our, lr=1e-3, weight_decay=1e-4, t_max=50, graph=graph)
+    # "alias": the graph reads the caller's input tensors in place, one captured graph per input set (two allowed
+    # here, the third batch goes through the copying graph)
+    our_step = FusedTrainStep(m_our, lr=1e-3, weight_decay=1e-4, t_max=50, graph=bool(graph),
+                              alias_inputs=(graph == "alias"), max_graphs=2)
     batches = [tuple(t.cuda() for t in data.synthetic_batch(4, 16, 3, 2, seed=s)) for s in range(3)]
-    for it in range(7):
+    for it in range(10 if graph == "alias" else 7):
         xx, yy, grid = batches[it % 3]
         l_ref = ref_step(xx, yy, grid)
         l_our = our_step(xx, yy, grid)
