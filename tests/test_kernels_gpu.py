@@ -515,3 +515,30 @@ def test_fwd_transform_tf32_mode(lib, monkeypatch):
     assert errs["tf32"][2] < TOL                    # dS itself is computed in fp32 in both modes
     assert errs["tf32"][0] > 10 * errs["fp32"][0], errs
     print("K1 tf32-mode errors (plain, premultiply):", f"{errs['tf32'][0]:.2e}", f"{errs['tf32'][1]:.2e}")
+
+
+def test_new_entry_points_reject_bad_arguments(lib):
+    """C-ABI error behaviour of the entry points added for the tensor-core / dataset paths: a negative code and a
+    message, never a silent fallback."""
+    L = lib.load()
+    z = torch.zeros(1 << 16, device="cuda")
+    p = z.data_ptr()
+    st = 0
+    # tcgen05 head backward: hidden width must be 128, C + bias column <= 24, V <= 4
+    assert L.fno_head_bwd_tc(p, p, p, p, p, p, p, p, p, p, p, p, 1, 8, 8, 10, 10, 24, 128, 2, st) < 0
+    assert b"C <= 23" in L.fno_last_error()
+    assert L.fno_head_bwd_tc(p, p, p, p, p, p, p, p, p, p, p, p, 1, 8, 8, 10, 10, 20, 64, 2, st) < 0
+    assert L.fno_head_bwd_tc(p, p, p, p, p, p, p, p, p, p, p, None, 1, 8, 8, 10, 10, 20, 128, 2, st) < 0   # no workspace
+    # fused bypass backward: needs the weights and the output tensor
+    assert L.fno_pointwise_bwd(p, p, None, p, p, p, p, 1, 20, 20, 64, st) < 0
+    # window gather: window longer than the trajectory
+    assert L.fno_window_gather(p, p, p, p, p, 2, 16, 5, 2, 5, 1, st) < 0
+    # math mode
+    assert L.fno_set_math_mode(7) < 0
+    assert lib.get_math_mode() == "fp32"
+    with pytest.raises(lib.FnoError):
+        lib.set_math_mode("bf16")
+    # device-resident dataset: trajectories shorter than a window
+    from fno_b200 import data
+    with pytest.raises(ValueError):
+        data.DeviceWindows(torch.zeros(2, 5, 8, 8, 2), initial_step=5, rollout=1, device="cuda")
