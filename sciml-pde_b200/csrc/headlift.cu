@@ -316,6 +316,8 @@ lift_bwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
 // ------------------------------------------------------------------------------------------
 constexpr int LB2_THREADS = 256;
 constexpr int LB2_SLICE = TILE / (LB2_THREADS / 32);    // pixels per warp and tile (8)
+constexpr int LB2_TP = TILE + 2;           // channel-row pitch: lanes read rows 4 cq + a of one pixel -> banks 8 cq + 2 a + px
+                                           // (pitch 68 put channel quads 0 / 2 / 4 on the same bank: 3-way conflicts)
 
 template <int NIT>
 __global__ void __launch_bounds__(LB2_THREADS, 3)
@@ -328,7 +330,7 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
   const int CQ = (C + 3) / 4, CR = 4 * CQ;
   const int nitems = CQ * FQ;
   // two tile buffers: tile i+1 is stored while tile i is multiplied -> ONE barrier per tile
-  const int buf_floats = TILE * FR + CR * TP;
+  const int buf_floats = TILE * FR + CR * LB2_TP;
   float* feat0 = sm;                          // [2][ [TILE][FR] | [CR][TP] channel rows (pad rows zero) ]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // constant columns: bias feature = 1, padding = 0
@@ -339,7 +341,7 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
       const int px = i / (FR - F), q = i - px * (FR - F);
       feat[px * FR + F + q] = (q == 0) ? 1.f : 0.f;
     }
-    for (int i = tid; i < TP * (CR - C); i += LB2_THREADS) dhs[C * TP + i] = 0.f;
+    for (int i = tid; i < LB2_TP * (CR - C); i += LB2_THREADS) dhs[C * LB2_TP + i] = 0.f;
   }
   int cq[NIT], fq[NIT];
   float acc[NIT][4][4];
@@ -427,7 +429,7 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
 #pragma unroll
     for (int u = 0; u < DR; ++u) {
       const int c = warp + u * (LB2_THREADS / 32);
-      if (c < C) *reinterpret_cast<float2*>(dhs + c * TP + 2 * lane) = dr[u];
+      if (c < C) *reinterpret_cast<float2*>(dhs + c * LB2_TP + 2 * lane) = dr[u];
     }
   };
   int bsel = 0;
@@ -451,9 +453,9 @@ lift_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ grid, co
       const int px = warp * LB2_SLICE + j;
 #pragma unroll
       for (int k = 0; k < NIT; ++k) {
-        const float* __restrict__ dq = dhs + 4 * cq[k] * TP + px;
+        const float* __restrict__ dq = dhs + 4 * cq[k] * LB2_TP + px;
         const float4 f = *reinterpret_cast<const float4*>(feat + px * FR + 4 * fq[k]);
-        const float dv[4] = {dq[0], dq[TP], dq[2 * TP], dq[3 * TP]}, fv[4] = {f.x, f.y, f.z, f.w};
+        const float dv[4] = {dq[0], dq[LB2_TP], dq[2 * LB2_TP], dq[3 * LB2_TP]}, fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -1019,7 +1021,7 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
     const bool aligned = (reinterpret_cast<size_t>(x) & 15) == 0;
     if ((T * V) % 4 == 0 && aligned && NIT <= 2 && C * (TILE / 2) <= 3 * LB2_THREADS && TILE * (T * V / 4) <= 2 * LB2_THREADS && TILE * G <= LB2_THREADS &&
         Wp % 2 == 0 && (reinterpret_cast<size_t>(dh) & 7) == 0) {
-      const size_t tile_bytes = 2 * sizeof(float) * ((size_t)TILE * FQ * 4 + (size_t)CQ * 4 * TP);   // double-buffered
+      const size_t tile_bytes = 2 * sizeof(float) * ((size_t)TILE * FQ * 4 + (size_t)CQ * 4 * LB2_TP);   // double-buffered
       const size_t red_bytes = sizeof(float) * (size_t)(LB2_THREADS / 32) * nitems * 16;
       const size_t smem2 = tile_bytes > red_bytes ? tile_bytes : red_bytes;
       const int ctas = tm0.total < LB_CTAS ? tm0.total : LB_CTAS;
