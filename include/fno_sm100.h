@@ -122,6 +122,27 @@ int fno_sc3d_inv_transform(const fno_plan* plan, const float* Y, const float* ad
                            float* s_out, float* out, void* work, long planes, int cmode,
                            float scale, int apply_gelu, fno_stream_t stream);
 
+/* ---- fused Fourier-layer output: K3 + 1x1-conv bypass + bias + GELU on the tensor cores --------- */
+/* Replaces, in ONE pass over the activation, everything after the mode mixing of a Fourier layer
+ * (fno/fno.py:76-92 zeros + slice-assign + irfft2, :162 w_l(x), :163 x1 + x2, :164 F.gelu):
+ *   s   = irfft2(scatter(Y)) + W a + bias        (pre-activation, optional output s_out)
+ *   out = gelu(s) if apply_gelu else s
+ * as a tcgen05 GEMM per row of the plane (layer2d_tc.cu): the contiguous-axis inverse DFT, the 1x1
+ * convolution and the bias share one accumulator in tensor memory (3xTF32 split: fp32-mode accuracy;
+ * FNO_MATH_TF32: single pass).  With transpose_w = 1, cmode = 0, scale = 1, bias = NULL and a = dS,
+ * Y = gX it is the data gradient of the layer: K3(gX) + W^T dS (autograd of :161-163).
+ *   Y [B, C, 2*m1, m2] c64,  a / s_out / out [B, C, H, W] f32 (a must not alias an output),
+ *   W [C, C] (conv weight viewed 2-D), bias [C] or NULL,
+ *   work: fno_layer2d_fused_workspace_bytes(plan, B, C) bytes (16-byte aligned).
+ * fno_layer2d_fused_supported: 1 if the plan geometry / width can run on this path (W <= 132,
+ * 2*m2 <= 32, C <= 31), else 0 -- callers then use fno_pointwise_fwd + fno_sc2d_inv_transform.     */
+int fno_layer2d_fused_supported(const fno_plan* plan, int C);
+size_t fno_layer2d_fused_workspace_bytes(const fno_plan* plan, int B, int C);
+int fno_layer2d_inv_fused(const fno_plan* plan, const float* Y, const float* a, const float* W,
+                          const float* bias, float* s_out, float* out, void* work, int B, int C,
+                          int cmode, float scale, int apply_gelu, int transpose_w,
+                          fno_stream_t stream);
+
 /* ---- 1x1-conv bypass (nn.Conv2d/3d(width, width, 1); fno/fno.py:131-134,162) ----------------- */
 /* out[b,o,p] = sum_i W[o,i] in[b,i,p] (+ bias[o]);  transpose != 0: out[b,i,p] = sum_o W[o,i] in[b,o,p]
  *   in [B, Cin, N], out [B, Cout, N], W [Co, Ci] (the conv weight viewed 2-D), N = pixels/sample */

@@ -302,6 +302,30 @@ int fno_sc3d_inv_transform(const fno_plan* plan, const float* Y, const float* ad
   return launch_inv2d(p, Z, addend, s_out, out, planes * p->D1, cmode, scale, apply_gelu, st);
 }
 
+int fno_layer2d_fused_supported(const fno_plan* plan, int C) {
+  const Plan* p = P(plan);
+  return (p != nullptr && p->nd == 2 && layer2d_tc_supported(p, C)) ? 1 : 0;
+}
+
+size_t fno_layer2d_fused_workspace_bytes(const fno_plan* plan, int B, int C) {
+  const Plan* p = P(plan);
+  if (p == nullptr || p->nd != 2) return 0;
+  return layer2d_tc_workspace_bytes(p, B, C);
+}
+
+int fno_layer2d_inv_fused(const fno_plan* plan, const float* Y, const float* a, const float* W, const float* bias,
+                          float* s_out, float* out, void* work, int B, int C, int cmode, float scale, int apply_gelu,
+                          int transpose_w, fno_stream_t stream) {
+  const Plan* p = P(plan);
+  if (!p || p->nd != 2 || !Y || !a || !W || !out || !work || B <= 0 || C <= 0) {
+    set_error("fno_layer2d_inv_fused: bad argument");
+    return FNO_E_ARG;
+  }
+  if (a == out || a == s_out) { set_error("fno_layer2d_inv_fused: the input may not alias an output"); return FNO_E_ARG; }
+  return launch_layer2d_tc(p, Y, a, W, bias, s_out, out, static_cast<float*>(work), B, C, cmode, scale, apply_gelu,
+                           transpose_w, static_cast<cudaStream_t>(stream));
+}
+
 int fno_mix_fwd(const fno_plan* plan, const float* X, const float* const* w, float* Y, int B, int Ci, int Co,
                 fno_stream_t stream) {
   const Plan* p = P(plan);

@@ -57,6 +57,11 @@ int launch_fwd2d_tcap(const Plan* p, const float* g, const float* preact, float*
 int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cudaStream_t st, bool attr_only);
 int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
                     cudaStream_t st, bool attr_only);
+bool layer2d_tc_supported(const Plan* p, int C);
+size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C);
+int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float* Wl, const float* bias, float* s_out,
+                      float* out, float* work, int B, int C, int cmode, float scale, int apply_gelu, int transpose_w,
+                      cudaStream_t st);
 size_t head_bwd_tc_workspace_bytes();
 int head_pad_zero(float* dh, int R_in, int W_in, int R_out, int Wp, long planes, cudaStream_t st);
 int launch_axis_fwd(const Plan* p, const float* S, float* X, long planes, long Q, cudaStream_t st);

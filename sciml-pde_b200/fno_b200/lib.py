@@ -66,6 +66,9 @@ def load():
             "fno_mix_bwd": (i, [vp, vp, vp, vpp, vp, vpp, i, i, i, vp]),
             "fno_sc2d_inv_transform": (i, [vp, vp, vp, vp, vp, l, i, f, i, vp]),
             "fno_sc3d_inv_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, i, vp]),
+            "fno_layer2d_fused_supported": (i, [vp, i]),
+            "fno_layer2d_fused_workspace_bytes": (C.c_size_t, [vp, i, i]),
+            "fno_layer2d_inv_fused": (i, [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, f, i, i, vp]),
             "fno_pointwise_fwd": (i, [vp, vp, vp, vp, i, i, i, l, i, vp]),
             "fno_pointwise_wgrad_workspace_bytes": (C.c_size_t, [i, i, i, l]),
             "fno_pointwise_wgrad": (i, [vp, vp, vp, vp, vp, i, i, i, l, vp]),
@@ -105,7 +108,8 @@ EXPORTED_SYMBOLS = (
     "fno_plan2d_create", "fno_plan3d_create", "fno_plan_destroy", "fno_plan_workspace_bytes",
     "fno_sc2d_fwd_transform", "fno_sc2d_fwd_workspace_bytes", "fno_sc2d_fwd_transform_ws",
     "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
-    "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_pointwise_fwd",
+    "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_layer2d_fused_supported",
+    "fno_layer2d_fused_workspace_bytes", "fno_layer2d_inv_fused", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad", "fno_pointwise_bwd",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
     "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
@@ -275,6 +279,47 @@ def inv_transform(plan: Plan, Y: torch.Tensor, *, addend: Optional[torch.Tensor]
         rc = lib.fno_sc3d_inv_transform(plan.handle, Y.data_ptr(), _ptr(addend), _ptr(s_out), out.data_ptr(),
                                         work.data_ptr(), planes, cmode, scale, int(apply_gelu), _stream())
     _check(rc, "fno_inv_transform")
+    return out
+
+
+# K3 with the 1x1-conv bypass folded into one tcgen05 GEMM per row (layer2d_tc.cu).  FNO_LAYER_TC=0 selects the
+# round-1 path (pointwise kernel + FP32 inverse transform).
+LAYER_TENSOR_CORES = os.environ.get("FNO_LAYER_TC", "1") != "0"
+
+
+def layer_fused_supported(plan: Plan, width: int) -> bool:
+    return bool(LAYER_TENSOR_CORES and plan.nd == 2 and load().fno_layer2d_fused_supported(plan.handle, int(width)))
+
+
+def layer_inv_fused(plan: Plan, Y: torch.Tensor, a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *,
+                    s_out: Optional[torch.Tensor] = None, cmode: int = 1, scale: Optional[float] = None,
+                    apply_gelu: bool = False, transpose: bool = False) -> torch.Tensor:
+    """act(K3(Y) + W a + bias) in one tensor-core pass over a (fno_layer2d_inv_fused).  a [B, C, H, W] f32,
+    Y [B, C, 2*m1, m2] c64, weight = the 1x1-conv weight [C, C, 1, 1]; transpose: W^T a (the layer's data gradient)."""
+    _require(Y, torch.complex64, "Y")
+    _require(a, torch.float32, "a")
+    _require(weight, torch.float32, "weight")
+    B, Cw = a.shape[0], a.shape[1]
+    if tuple(a.shape[2:]) != plan.spatial or tuple(Y.shape) != (B, Cw) + plan.spec_shape:
+        raise FnoError(f"layer_inv_fused: a {tuple(a.shape)} / Y {tuple(Y.shape)} do not match plan {plan.spatial} {plan.spec_shape}")
+    if weight.shape[0] != Cw or weight.shape[1] != Cw:
+        raise FnoError(f"layer_inv_fused: weight {tuple(weight.shape)} is not [{Cw}, {Cw}, ...]")
+    if bias is not None:
+        _require(bias, torch.float32, "bias")
+    if s_out is not None:
+        _require(s_out, torch.float32, "s_out")
+    if scale is None:
+        scale = 1.0 / plan.npix
+    lib = load()
+    nbytes = lib.fno_layer2d_fused_workspace_bytes(plan.handle, B, Cw)
+    if nbytes == 0:
+        raise FnoError("layer_inv_fused: geometry not supported by the tensor-core layer kernel")
+    work = torch.empty(nbytes // 4, dtype=torch.float32, device=a.device)
+    out = torch.empty_like(a)
+    rc = lib.fno_layer2d_inv_fused(plan.handle, Y.data_ptr(), a.data_ptr(), weight.data_ptr(), _ptr(bias), _ptr(s_out),
+                                   out.data_ptr(), work.data_ptr(), B, Cw, cmode, scale, int(apply_gelu), int(transpose),
+                                   _stream())
+    _check(rc, "fno_layer2d_inv_fused")
     return out
 
 

@@ -98,25 +98,34 @@ class FourierLayerFn(torch.autograd.Function):
         wl = wl.contiguous()
         plan = _plan_for(a, weights)
         training = any(ctx.needs_input_grad)
-        if OVERLAP or OVERLAP_FWD:
-            main, side = torch.cuda.current_stream(), _side_stream(a.device)
-            lin = torch.empty((a.shape[0], wl.shape[0]) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                lib.pointwise_fwd(a, wl, bl, out=lin)
+        fused = lib.layer_fused_supported(plan, a.shape[1]) and wl.shape[0] == wl.shape[1] == a.shape[1]
+        if fused:
+            # K1 -> K2 -> one tensor-core pass: K3 + bypass + bias + GELU (layer2d_tc.cu); `lin` never exists
             X = lib.fwd_transform(plan, a)
             Y = lib.mix_fwd(plan, X, weights)
-            main.wait_stream(side)
+            s = torch.empty_like(a) if (training and apply_gelu) else None
+            out = lib.layer_inv_fused(plan, Y, a, wl, bl, s_out=s, cmode=1, apply_gelu=bool(apply_gelu))
         else:
-            lin = lib.pointwise_fwd(a, wl, bl)
-            X = lib.fwd_transform(plan, a)
-            Y = lib.mix_fwd(plan, X, weights)
-        s = torch.empty_like(lin) if (training and apply_gelu) else None
-        out = lib.inv_transform(plan, Y, addend=lin, s_out=s, out=lin, cmode=1, apply_gelu=apply_gelu)
+            if OVERLAP or OVERLAP_FWD:
+                main, side = torch.cuda.current_stream(), _side_stream(a.device)
+                lin = torch.empty((a.shape[0], wl.shape[0]) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    lib.pointwise_fwd(a, wl, bl, out=lin)
+                X = lib.fwd_transform(plan, a)
+                Y = lib.mix_fwd(plan, X, weights)
+                main.wait_stream(side)
+            else:
+                lin = lib.pointwise_fwd(a, wl, bl)
+                X = lib.fwd_transform(plan, a)
+                Y = lib.mix_fwd(plan, X, weights)
+            s = torch.empty_like(lin) if (training and apply_gelu) else None
+            out = lib.inv_transform(plan, Y, addend=lin, s_out=s, out=lin, cmode=1, apply_gelu=apply_gelu)
         if training:
             ctx.plan = plan
             ctx.apply_gelu = bool(apply_gelu)
             ctx.has_bias = bl is not None
+            ctx.fused = fused
             ctx.save_for_backward(a, wl, X, s if s is not None else a.new_empty(0), *weights)
         return out
 
@@ -137,6 +146,15 @@ class FourierLayerFn(torch.autograd.Function):
         gwl = gbl = None
         forked = False
         ga_lin = None
+        if ctx.fused:
+            # bypass weight / bias gradient, then K2', then the data gradient K3(gX) + Wl^T dS in one tensor-core pass
+            if need_wl or (need_bl and ctx.has_bias):
+                gwl, gbl = lib.pointwise_wgrad(ds, a, wl.shape, need_bias=ctx.has_bias)
+            gX, gws = lib.mix_bwd(plan, X, gY, weights, need_gx=need_ga, need_gw=need_gw)
+            ga = lib.layer_inv_fused(plan, gX, ds, wl, None, cmode=0, scale=1.0, transpose=True) if need_ga else None
+            if gws is None:
+                gws = [None] * len(weights)
+            return (ga, gwl if need_wl else None, gbl if (need_bl and ctx.has_bias) else None, None, *gws)
         if need_ga and need_wl and not OVERLAP:
             # weight, bias and data gradient of the bypass in one pass over ds (fno_pointwise_bwd)
             ga_lin, gwl, gbl = lib.pointwise_bwd(ds, a, wl, need_bias=ctx.has_bias)

@@ -89,6 +89,65 @@ def test_inv_transform_fused_epilogue(lib, B, C, H, W, m1, m2, gelu):
     assert O.rel_err(out.cpu().numpy(), ref) < TOL
 
 
+LAYER_TC_CASES = [
+    # B, C, H, W, m1, m2
+    (2, 3, 10, 9, 3, 4),          # odd W, partial lane tile
+    (2, 4, 12, 12, 6, 7),         # touching corners, Nyquist column
+    (3, 5, 34, 34, 12, 12),
+    (7, 3, 33, 31, 5, 9),         # odd H and W, 2*m2 = 18 -> padded K
+    (2, 20, 130, 130, 12, 12),    # cfg 1: 128 lanes + 2 edge columns, width 20
+    (1, 8, 16, 132, 4, 16),       # 4 edge columns, K padding of the bypass part
+    (1, 31, 20, 64, 5, 8),        # widest supported layer
+    (1, 5, 64, 70, 12, 12),       # a 3-D slice of cfg 4
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", LAYER_TC_CASES)
+@pytest.mark.parametrize("gelu", [False, True])
+def test_layer_inv_fused_tensor_core(lib, B, C, H, W, m1, m2, gelu):
+    """fno_layer2d_inv_fused: K3 + 1x1-conv bypass + bias (+ GELU) as one tcgen05 GEMM per row vs the fp64 oracle
+    (fno/fno.py:161-164)."""
+    rng = np.random.default_rng(H * 100 + W + C)
+    Y = cplx(rng, (B, C, 2 * m1, m2), scale=30.0)
+    a = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    wl = (rng.standard_normal((C, C, 1, 1)) / np.sqrt(C)).astype(np.float32)
+    bl = rng.standard_normal(C).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    assert lib.layer_fused_supported(plan, C)
+    at = dev(a)
+    s_out = torch.empty_like(at)
+    out = lib.layer_inv_fused(plan, dev(Y), at, dev(wl), dev(bl), s_out=s_out, cmode=1, apply_gelu=gelu)
+    s_ref = O.inv_transform(Y, (H, W), cmode=1) + O.pointwise_conv(a, wl, bl)
+    assert O.rel_err(s_out.cpu().numpy(), s_ref) < TOL
+    ref = O.gelu(s_ref) if gelu else s_ref
+    assert O.rel_err(out.cpu().numpy(), ref) < TOL
+    assert torch.equal(at.cpu(), torch.from_numpy(a))          # the input is read only
+
+
+@pytest.mark.parametrize("B,C,H,W,m1,m2", LAYER_TC_CASES)
+def test_layer_inv_fused_adjoint(lib, B, C, H, W, m1, m2):
+    """Data gradient of a Fourier layer in one pass: K3(gX; c = 1, no 1/HW) + Wl^T dS."""
+    rng = np.random.default_rng(H * 100 + W + C + 1)
+    gX = cplx(rng, (B, C, 2 * m1, m2))
+    ds = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    wl = (rng.standard_normal((C, C, 1, 1)) / np.sqrt(C)).astype(np.float32)
+    plan = lib.get_plan(torch.device("cuda", 0), (H, W), (m1, m2))
+    ga = lib.layer_inv_fused(plan, dev(gX), dev(ds), dev(wl), None, cmode=0, scale=1.0, transpose=True)
+    ref = O.inv_transform(gX, (H, W), cmode=0, scale=1.0) + np.einsum("oi,bohw->bihw", wl[:, :, 0, 0].astype(np.float64), ds)
+    assert O.rel_err(ga.cpu().numpy(), ref) < TOL
+
+
+def test_layer_inv_fused_rejects_bad_arguments(lib):
+    plan = lib.get_plan(torch.device("cuda", 0), (300, 300), (12, 12))
+    assert not lib.layer_fused_supported(plan, 20)                # W = 300 does not fit one lane tile
+    plan = lib.get_plan(torch.device("cuda", 0), (34, 34), (12, 12))
+    assert not lib.layer_fused_supported(plan, 40)                # width + bias column > 32
+    a = torch.zeros(1, 5, 34, 34, device="cuda")
+    with pytest.raises(lib.FnoError):
+        lib.layer_inv_fused(plan, torch.zeros(1, 5, 24, 11, dtype=torch.complex64, device="cuda"), a,
+                            torch.zeros(5, 5, 1, 1, device="cuda"), None)
+
+
 @pytest.mark.parametrize("B,C,H,W,m1,m2", [(2, 3, 10, 9, 3, 4), (2, 3, 130, 130, 12, 12)])
 def test_fwd_transform_gelu_grad_prologue(lib, B, C, H, W, m1, m2):
     """bwd_pre: transform of g * gelu'(s), storing dS."""
