@@ -176,6 +176,30 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
     }
   }
 }
+// polling wait (mbarrier.test_wait never suspends the warp): for hand-offs on the critical path of a short
+// pipeline step, where the wake-up latency of a parked warp is comparable to the step itself.  Same 4 s bound.
+__device__ __forceinline__ void mbar_wait_spin(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_u32(bar);
+  unsigned long long t0 = 0;
+#pragma unroll 1
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 0xfffffu) == 0xfffffu) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),

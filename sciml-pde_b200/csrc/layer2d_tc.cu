@@ -20,16 +20,37 @@
 // pointwise kernel of round 1 are gone; the activation is read once and each output written once.
 //
 // The last W - 128 columns of a row (2 for the 130-wide padded planes of cfg 1) do not fit the 128 TMEM lanes; an
-// "edge" warp computes them on the FP32 pipes from the same shared-memory operands.
+// "edge" warp computes them on the FP32 pipes, 32 rows at a time (lane = row), independently of the pipeline.
+//
+// Pipeline (per CTA, persistent over a contiguous range of rows; every hand-off is an mbarrier):
+//   2 B-prep warps   (one per row parity) bulk-copy raw T2 tiles into a 4-deep ring and    raw_full, mma_done -> b_ready
+//                    split them hi / lo into the operand buffers (the proxy fence this needs is why they are
+//                    separate warps: it is a MEMBAR that would wait for the converters' prefetched loads)
+//   8 converter warps  (lane quadrant x row parity) activation columns -> TMEM with wide     mma_done -> a_ready
+//                    tcgen05.st, 2 own rows of loads in flight
+//   MMA warp         18 tcgen05.mma per row into a double-buffered accumulator         b_ready, a_ready, d_free -> mma_done
+//   8 epilogue warps tcgen05.ld, GELU, stores                                          mma_done -> d_free
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace fno {
 namespace {
 
+// -DL2_TRACE: CTA 0 records clock64 at the pipeline hand-offs of its first 64 rows (tools only; off in the product build)
+#ifdef L2_TRACE
+#define L2TR(ev, it) do { if (p.trace != nullptr && blockIdx.x == 0 && lane == 0 && (it) < 64) p.trace[(it) * 16 + (ev)] = clock64(); } while (0)
+#else
+#define L2TR(ev, it) do { } while (0)
+#endif
+#ifdef L2_TRACE
+#define L2DBG(bit) (p.dbg & (bit))
+#else
+#define L2DBG(bit) 0
+#endif
 constexpr int L2_RMAX = 4;        // edge columns (W - 128) handled on the FP32 pipes
-constexpr int L2_EPF = 4;         // prefetch depth (tiles) of the edge warp's activation loads
 constexpr int L2_NR = 4;          // T2 tiles in flight (bulk copies into a shared-memory ring)
-constexpr int L2_PD = 3;          // tiles of activation loads in flight per converter thread
+constexpr int L2_PD = 2;          // own rows of activation loads in flight per converter thread (= 4 rows ahead)
 
 __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -53,8 +74,21 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
   constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
   const int q = threadIdx.x % m2, cl = threadIdx.x / m2;
   const int c = blockIdx.z * 8 + cl;
-  if (cl >= 8 || c >= C) return;
+  if (cl >= 8) return;
   const int bd = blockIdx.x;                  // b * D1 + d1
+  if (c >= C) {
+    // rows of the last 8-row group beyond the width: zeros (the operand tile is consumed whole)
+    const int NPz = H / 2 + 1;
+    const int tz0 = blockIdx.y * TL, tz1 = (tz0 + TL < NPz) ? tz0 + TL : NPz;
+    const int eo = (c >> 3) * KQ * 8 + (c & 7) * 4;
+    float* __restrict__ bz = T2g + (size_t)bd * H * tile_floats;
+    for (int t = tz0; t < tz1; ++t)
+      for (int k = q; k < KQ; k += m2) {
+        bz[(size_t)t * tile_floats + eo + (k >> 2) * 32 + (k & 3)] = 0.f;
+        if (t != 0 && 2 * t != H) bz[(size_t)(H - t) * tile_floats + eo + (k >> 2) * 32 + (k & 3)] = 0.f;
+      }
+    return;
+  }
   const int b = bd / D1, d1 = bd - b * D1;
   const size_t plane = ((size_t)b * C + c) * D1 + d1;
   const float2* __restrict__ Yp = Y + plane * (size_t)(2 * m1) * m2 + q;
@@ -94,10 +128,12 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
     float* __restrict__ o = base + (size_t)t * tile_floats;
     o[o_re] = sc * (er - odr);
     o[o_im] = -sc * (ei + odi);
+    for (int k = 2 * m2 + q; k < KQ; k += m2) o[eoff + (k >> 2) * 32 + (k & 3)] = 0.f;      // K padding
     if (t != 0 && 2 * t != H) {
       float* __restrict__ o2 = base + (size_t)(H - t) * tile_floats;
       o2[o_re] = sc * (er + odr);
       o2[o_im] = -sc * (ei - odi);
+      for (int k = 2 * m2 + q; k < KQ; k += m2) o2[eoff + (k >> 2) * 32 + (k & 3)] = 0.f;
     }
   }
 }
@@ -107,17 +143,17 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
 // ------------------------------------------------------------------------------------------------------
 template <int KA, int NPAD, int CWQ>
 struct L2Cfg {
-  static constexpr int KC = (((KA + CWQ - 1) / CWQ) + 3) & ~3;   // A columns per converter warp
+  static_assert(CWQ == 2, "two converter warps per lane quadrant: one per row parity");
   static constexpr int EW = NPAD / 16;                           // epilogue warps per lane quadrant
   static constexpr int CONV_WARPS = 4 * CWQ;
   static constexpr int EPI_WARP0 = CONV_WARPS;
   static constexpr int EPI_WARPS = 4 * EW;
   static constexpr int MMA_WARP = CONV_WARPS + EPI_WARPS;
-  static constexpr int BPREP_WARP = MMA_WARP + 1;
-  static constexpr int EDGE_WARP = MMA_WARP + 2;
-  static constexpr int THREADS = 32 * (MMA_WARP + 3);
-  static constexpr int F4_PER_LANE = NPAD / 4;                   // float4 of a T2 tile per B-prep lane (KQ <= 32)
-  static constexpr int ECH = NPAD / 32;                          // channels per edge-warp lane
+  static constexpr int EDGE_WARP = MMA_WARP + 1;
+  static constexpr int BPREP_WARP0 = MMA_WARP + 2;               // 2 warps: raw T2 tile -> hi / lo operand buffers
+  static constexpr int BPREP_WARPS = 2;
+  static constexpr int NFB = NPAD / 4;                           // float4 of a T2 tile per B-prep lane (KQ <= 32)
+  static constexpr int THREADS = 32 * (MMA_WARP + 2 + BPREP_WARPS);
   static constexpr unsigned TM_COLS = (2 * 32 + 4 * KA + 2 * NPAD <= 256) ? 256u : 512u;
 };
 
@@ -134,55 +170,75 @@ struct L2Args {
   long total_tiles;     // B * RS
   int transpose_w, apply_gelu, single;
   FastDiv rs_div;
+  unsigned long long* trace;
+  int dbg;   // L2_TRACE builds only: 1 no epilogue stores, 2 no activation loads, 4 no MMAs, 8 no edge, 16 no STTM, 32 no LDTM
 };
 
-template <int KA, int NPAD, int CWQ>
+template <int V>
+struct IC { static constexpr int value = V; };
+
+// waits: the single MMA / producer warps poll (they are the critical path and cost one warp's issue slots), the 16
+// converter / epilogue warps park (polling would take the issue slots the working warps of their sub-partition need)
+#ifndef L2WAIT_HOT
+#define L2WAIT_HOT mbar_wait_spin
+#endif
+#ifndef L2WAIT_COLD
+#define L2WAIT_COLD mbar_wait
+#endif
+
+// CX: compile-time width (0 = run-time p.C, every channel loop predicated); GELU / SOUT: epilogue form
+template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT>
 __global__ void __launch_bounds__(L2Cfg<KA, NPAD, CWQ>::THREADS, 1)
 layer2d_tc_kernel(const L2Args p) {
   using Cfg = L2Cfg<KA, NPAD, CWQ>;
-  constexpr int KC = Cfg::KC;
   extern __shared__ __align__(128) unsigned char lsm[];
-  const int KQ = p.KQ, C = p.C, W = p.W;
+  const int KQ = p.KQ, W = p.W;
+  const int C = CX > 0 ? CX : p.C;
+  const int CP = (C + 3) & ~3;
   const int t2_tile = NPAD * KQ;                          // floats of one hi (or lo) T2 operand tile
   float* bT2 = reinterpret_cast<float*>(lsm);             // [2 stages][hi | lo][NPAD * KQ]
   float* bW = bT2 + 4 * t2_tile;                          // [hi | lo][NPAD * KA]
-  float* eW = bW + 2 * NPAD * KA;                         // [C][C + 1] raw weight (edge warp)
-  float* eB = eW + ((C * (C + 1) + 3) & ~3);              // [NPAD] bias
+  float* eW = bW + 2 * NPAD * KA;                         // [C][CP] raw weight (edge warp), zero padded rows
+  float* eB = eW + C * CP;                                // [NPAD] bias
   float* eF = eB + NPAD;                                  // [L2_RMAX][KQ] twiddles of the edge columns
-  float* eA = eF + L2_RMAX * KQ;                          // [NPAD][L2_RMAX] edge activations of the current tile
-  float* ring = eA + NPAD * L2_RMAX;                      // [L2_NR][tile_floats] raw T2 tiles (bulk-copy destination)
+  float* ring = eF + L2_RMAX * KQ;                        // [L2_NR][tile_floats] raw T2 tiles (bulk-copy destination)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<size_t>(ring + (size_t)L2_NR * p.tile_floats) + 15) & ~size_t(15));
-  unsigned long long* a_ready = bars;        // [2] converters wrote A buffer s
-  unsigned long long* b_ready = bars + 2;    // [2] T2 operand tile s is split and staged
-  unsigned long long* mma_done = bars + 4;   // [2] MMAs of the tile on buffers s complete (A / B free, D full)
-  unsigned long long* d_free = bars + 6;     // [2] accumulator s read back
-  unsigned long long* edge_done = bars + 8;  // [2] edge warp done with T2 tile s
-  unsigned long long* raw_full = bars + 10;  // [L2_NR] bulk copy of a raw T2 tile landed
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 10 + L2_NR);
+  unsigned long long* a_ready = bars;                  // [2] converters wrote A buffer s
+  unsigned long long* mma_done = bars + 2;             // [2] MMAs of the tile on buffers s complete (A / B free, D full)
+  unsigned long long* d_free = bars + 4;               // [2] accumulator s read back
+  unsigned long long* b_ready = bars + 6;              // [2] T2 operand tile s is split and staged
+  unsigned long long* raw_full = bars + 8;             // [L2_NR] bulk copy of a raw T2 tile landed
+  unsigned long long* f_ready = bars + 8 + L2_NR;      // [1] the twiddle columns of A are in tensor memory (once)
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 9 + L2_NR);
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int Wm = W < 128 ? W : 128;          // columns on the tensor cores
   const int r_edge = W - Wm;                 // columns on the edge warp
   const int m2x2 = 2 * p.m2;
-  const size_t cs = (size_t)p.RS * W;        // channel stride
+  const unsigned RS = (unsigned)p.RS;
+  const size_t cs = (size_t)RS * W;          // channel stride (floats)
+  const size_t bs = cs * C;                  // sample stride
+  const FastDiv rsd = p.rs_div;
   const long t_begin = (p.total_tiles * (long)blockIdx.x) / (long)gridDim.x;          // total_tiles < 2^32, grid <= 148
   const long t_end = (p.total_tiles * (long)(blockIdx.x + 1)) / (long)gridDim.x;
   const int ntl = (int)(t_end - t_begin);
+  const int single = p.single;
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_ready + s, Cfg::CONV_WARPS);
-      mbar_init(b_ready + s, 1);
+      mbar_init(a_ready + s, 4);                     // the four lane-quadrant converter warps of parity s
       mbar_init(mma_done + s, 1);
       mbar_init(d_free + s, Cfg::EPI_WARPS);
-      mbar_init(edge_done + s, 1);
+      mbar_init(b_ready + s, 1);
     }
     for (int s = 0; s < L2_NR; ++s) mbar_init(raw_full + s, 1);
+    mbar_init(f_ready, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == Cfg::MMA_WARP) tmem_alloc(tmem_slot, Cfg::TM_COLS);
-  // constant operands: Wl (+ bias row) hi / lo in the K-major core-matrix layout, zero T2 tiles (rows >= C stay zero)
+  // constant operands: Wl (+ bias row) hi / lo in the K-major core-matrix layout; T2 operand rows beyond the tile's
+  // row groups stay zero
   for (int i = tid; i < 4 * t2_tile; i += Cfg::THREADS) bT2[i] = 0.f;
   for (int i = tid; i < NPAD * KA; i += Cfg::THREADS) {
     const int n = i / KA, k = i - n * KA;
@@ -197,9 +253,9 @@ layer2d_tc_kernel(const L2Args p) {
     bW[off] = hi;
     bW[NPAD * KA + off] = lo;
   }
-  for (int i = tid; i < C * C; i += Cfg::THREADS) {
-    const int n = i / C, k = i - n * C;
-    eW[n * (C + 1) + k] = __ldg(p.Wl + (p.transpose_w ? (size_t)k * C + n : (size_t)n * C + k));
+  for (int i = tid; i < C * CP; i += Cfg::THREADS) {
+    const int n = i / CP, k = i - n * CP;
+    eW[i] = (k < C) ? __ldg(p.Wl + (p.transpose_w ? (size_t)k * C + n : (size_t)n * C + k)) : 0.f;
   }
   for (int i = tid; i < NPAD; i += Cfg::THREADS) eB[i] = (i < C && p.bias != nullptr) ? __ldg(p.bias + i) : 0.f;
   for (int i = tid; i < L2_RMAX * KQ; i += Cfg::THREADS) {
@@ -214,72 +270,93 @@ layer2d_tc_kernel(const L2Args p) {
   const unsigned TM_FHI = 0, TM_FLO = (unsigned)KQ, TM_A = 2u * KQ, TM_D = 2u * KQ + 4u * KA;
 
   if (warp < Cfg::CONV_WARPS) {
-    // ---- converters: lane = w, KC columns of the bypass part of A -----------------------------------
-    const int quad = warp & 3, cw = warp >> 2;
+    // ---- converters: lane = w.  Warp (quadrant, parity) owns ALL bypass columns of its 32 lanes for the rows of its
+    // parity, i.e. A buffer s = parity: tcgen05.st costs ~15-30 cycles of the SM's tensor-memory store port per
+    // INSTRUCTION whatever its width (48 x4 stores per row made the converters the bottleneck), so a row is written
+    // with x16 / x8 stores -- 4 per warp.  L2_PD own rows (2 L2_PD rows ahead) of loads are in flight per thread.
+    const int quad = warp & 3, par = warp >> 2;
     const int w = quad * 32 + lane;
     const bool wv = w < Wm;
     const unsigned ta = tmem_base + ((unsigned)(quad * 32) << 16);
-    if (cw == 0) {
+    if (par == 0) {
       // twiddle columns, once: F[w, q'] = twW[q'][w]
-      for (int g = 0; g < KQ / 4; ++g) {
-        float hi[4], lo[4];
+      for (int g = 0; g < KQ / 8; ++g) {
+        float hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = 4 * g + e;
+        for (int e = 0; e < 8; ++e) {
+          const int k = 8 * g + e;
           const float v = (wv && k < m2x2) ? __ldg(p.twW + (size_t)k * p.WP + w) : 0.f;
           split_tf32(v, hi[e], lo[e]);
         }
-        tmem_st4(ta + TM_FHI + 4u * g, hi);
-        tmem_st4(ta + TM_FLO + 4u * g, lo);
-      }
-      tmem_st_wait();
-    }
-    const int col0 = cw * KC;
-    float pre[L2_PD][KC];
-    auto load_tile = [&](int it, float (&r)[KC]) {
-      if (it >= ntl) return;
-      const long T = t_begin + it;
-      const unsigned b = p.rs_div.div((unsigned)T);
-      const unsigned row = (unsigned)T - b * (unsigned)p.RS;
-      const float* __restrict__ src = p.a + ((size_t)b * C * p.RS + row) * W + w + (size_t)col0 * cs;
-#pragma unroll
-      for (int i = 0; i < KC; ++i) {
-        r[i] = (wv && col0 + i < C) ? __ldg(src) : 0.f;
-        src += cs;
-      }
-    };
-    auto convert_tile = [&](int it, float (&r)[KC]) {
-      const int s = it & 1;
-      const unsigned ph = ((unsigned)it >> 1) & 1u;
-      mbar_wait(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read A buffer s
-      tc_fence_after();
-      const unsigned ah = ta + TM_A + (unsigned)(s * 2 * KA) + (unsigned)col0, al = ah + KA;
-#pragma unroll
-      for (int g = 0; g < KC / 4; ++g) {
-        if (col0 + 4 * g >= KA) break;
-        float hi[4], lo[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = col0 + 4 * g + e;
-          const float v = (col == C) ? 1.0f : r[4 * g + e];    // constant-one column carries the bias
-          split_tf32(v, hi[e], lo[e]);
-        }
-        tmem_st4(ah + 4u * g, hi);
-        if (!p.single) tmem_st4(al + 4u * g, lo);
+        tmem_st8(ta + TM_FHI + 8u * g, hi);
+        tmem_st8(ta + TM_FLO + 8u * g, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(f_ready);
+    }
+    constexpr int NLD = CX > 0 ? CX : KA - 1;                 // channel slots per thread (C <= KA - 1)
+    const float* __restrict__ abase = p.a + w;
+    const unsigned ah = ta + TM_A + (unsigned)(par * 2 * KA), al = ah + KA;
+    const int s = par;
+    float pre[L2_PD][NLD];
+    auto load_tile = [&](int it, float (&r)[NLD]) {
+      if (it >= ntl) return;
+      const unsigned T = (unsigned)(t_begin + it);
+      const unsigned b = rsd.div(T);
+      const unsigned row = T - b * RS;
+      const float* __restrict__ src = abase + (size_t)b * bs + (size_t)row * W;
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) {
+        r[i] = (wv && i < C && !L2DBG(2)) ? __ldg(src) : 0.f;
+        src += cs;
+      }
+    };
+    auto column = [&](const float (&r)[NLD], int col) -> float {      // col is a compile-time constant after unrolling
+      return col < NLD ? ((CX == 0 && col == C) ? 1.0f : r[col < NLD ? col : 0]) : (col == C ? 1.0f : 0.f);
+    };
+    auto convert_tile = [&](int it, float (&r)[NLD]) {
+      const unsigned ph = ((unsigned)it >> 1) & 1u;
+      L2WAIT_COLD(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read A buffer s
+      if (warp == 0) L2TR(0, it);
+      tc_fence_after();
+      if (warp == 0) L2TR(1, it);
+#pragma unroll
+      for (int c0 = 0; c0 < KA; c0 += 16) {
+        if (KA - c0 >= 16) {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) split_tf32(column(r, c0 + e), hi[e], lo[e]);
+          if (!L2DBG(16)) {
+            tmem_st16(ah + (unsigned)c0, hi);
+            if (!single) tmem_st16(al + (unsigned)c0, lo);
+          }
+        } else {
+          float hi[8], lo[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) split_tf32(column(r, c0 + e), hi[e], lo[e]);
+          if (!L2DBG(16)) {
+            tmem_st8(ah + (unsigned)c0, hi);
+            if (!single) tmem_st8(al + (unsigned)c0, lo);
+          }
+        }
+      }
+      if (warp == 0) L2TR(3, it);
+      tmem_st_wait();                              // (no fence.proxy.async here: it compiles to MEMBAR.ALL.CTA, which would
+      tc_fence_before();                           //  wait for this warp's prefetched global loads every tile)
+      __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + s);
+      if (warp == 0) L2TR(5, it);
     };
 #pragma unroll
-    for (int d = 0; d < L2_PD; ++d) load_tile(d, pre[d]);
-    for (int it = 0; it < ntl; it += L2_PD) {
+    for (int d = 0; d < L2_PD; ++d) load_tile(par + 2 * d, pre[d]);
+    for (int it = par; it < ntl; it += 2 * L2_PD) {
 #pragma unroll
       for (int d = 0; d < L2_PD; ++d) {
-        if (it + d < ntl) {
-          convert_tile(it + d, pre[d]);
-          load_tile(it + d + L2_PD, pre[d]);
+        if (it + 2 * d < ntl) {
+          convert_tile(it + 2 * d, pre[d]);
+          load_tile(it + 2 * d + 2 * L2_PD, pre[d]);
         }
       }
     }
@@ -287,68 +364,90 @@ layer2d_tc_kernel(const L2Args p) {
     // ---- epilogue: thread = w, a slice of the output channels ------------------------------------------
     const int ew = warp - Cfg::EPI_WARP0;
     const int quad = ew & 3, e = ew >> 2;
-    const int CPW = (C + Cfg::EW - 1) / Cfg::EW;
-    const int c0 = e * CPW;
-    const int cn = (C - c0 < CPW) ? C - c0 : CPW;
     const int w = quad * 32 + lane;
     const bool wv = w < Wm;
-    for (int it = 0; it < ntl; ++it) {
-      const int s = it & 1;
-      const unsigned ph = ((unsigned)it >> 1) & 1u;
-      const long T = t_begin + it;
-      const unsigned b = p.rs_div.div((unsigned)T);
-      const unsigned row = (unsigned)T - b * (unsigned)p.RS;
-      mbar_wait(mma_done + s, ph);
-      tc_fence_after();
-      float v[16];
-      tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + TM_D + (unsigned)(s * NPAD + c0), v);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(d_free + s);
-      size_t off = (((size_t)b * C + c0) * p.RS + row) * W + w;
-      if (wv) {
+    auto role = [&](auto Ec) {
+      constexpr int E = decltype(Ec)::value;
+      const int CPW = (C + Cfg::EW - 1) / Cfg::EW;
+      const int c0 = E * CPW;
+      const int cn = (C - c0 < CPW) ? (C - c0 > 0 ? C - c0 : 0) : CPW;
+      float* __restrict__ obase = p.out + w + (size_t)c0 * cs;
+      float* __restrict__ sbase = SOUT ? p.s_out + w + (size_t)c0 * cs : nullptr;
+      const unsigned td = tmem_base + ((unsigned)(quad * 32) << 16) + TM_D + (unsigned)c0;
+      for (int it = 0; it < ntl; ++it) {
+        const int s = it & 1;
+        const unsigned ph = ((unsigned)it >> 1) & 1u;
+        const unsigned T = (unsigned)(t_begin + it);
+        const unsigned b = rsd.div(T);
+        const unsigned row = T - b * RS;
+        const size_t toff = (size_t)b * bs + (size_t)row * W;
+        L2WAIT_COLD(mma_done + s, ph);
+        if (ew == 0) L2TR(9, it);
+        tc_fence_after();
+        float v[16];
+        if (!L2DBG(32)) tmem_ld16(td + (unsigned)(s * NPAD), v);
+        else { for (int i = 0; i < 16; ++i) v[i] = (float)i; }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_free + s);
+        if (ew == 0) L2TR(10, it);
+        if (wv && !L2DBG(1)) {
+          float* __restrict__ po = obase + toff;
+          float* __restrict__ ps = SOUT ? sbase + toff : nullptr;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < cn) {
-            const float x = v[i];
-            if (p.s_out != nullptr) p.s_out[off] = x;
-            p.out[off] = p.apply_gelu ? gelu_fast(x) : x;
-            off += cs;
+          for (int i = 0; i < 16; ++i) {
+            if (i < cn) {
+              const float x = v[i];
+              if (SOUT) { *ps = x; ps += cs; }
+              *po = GELU ? gelu_fast(x) : x;
+              po += cs;
+            }
           }
         }
+        if (ew == 0) L2TR(11, it);
       }
-    }
+    };
+    if (e == 0) role(IC<0>{});
+    else if (e == 1) role(IC<1>{});
+    else if (e == 2) role(IC<2>{});
+    else role(IC<3>{});
   } else if (warp == Cfg::MMA_WARP) {
     // ---- MMA issuer (whole warp converged, one elected lane issues) ------------------------------------
     constexpr unsigned idesc = umma_idesc_tf32(128, NPAD, 0, 0);
     const unsigned long long d_wh = umma_desc(bW, 128, KA * 32), d_wl = umma_desc(bW + NPAD * KA, 128, KA * 32);
-    const int single = p.single;
+    const unsigned long long d_t0 = umma_desc(bT2, 128, KQ * 32);
+    const unsigned long long t2d = (unsigned long long)((t2_tile * 4) >> 4);       // descriptor step between T2 buffers
+    const int nkq = KQ / 8;
+    L2WAIT_HOT(f_ready, 0u);
     for (int it = 0; it < ntl; ++it) {
       const int s = it & 1;
       const unsigned ph = ((unsigned)it >> 1) & 1u;
       const unsigned td = tmem_base + TM_D + (unsigned)(s * NPAD);
-      const unsigned long long d_th = umma_desc(bT2 + (size_t)(2 * s) * t2_tile, 128, KQ * 32);
-      const unsigned long long d_tl = umma_desc(bT2 + (size_t)(2 * s + 1) * t2_tile, 128, KQ * 32);
-      mbar_wait(d_free + s, ph ^ 1u);
-      mbar_wait(b_ready + s, ph);
-      tc_fence_after();
-      __syncwarp();
-#pragma unroll 1
-      for (int ks = 0; ks < KQ / 8; ++ks) {
-        const unsigned long long fo = (unsigned long long)(ks * 16);
-        const unsigned fh = tmem_base + TM_FHI + 8u * ks, fl = tmem_base + TM_FLO + 8u * ks;
-        if (!single) {
-          tc_mma_tf32_ts_elect(td, fl, d_th + fo, idesc, ks != 0);
-          tc_mma_tf32_ts_elect(td, fh, d_tl + fo, idesc, 1u);
-        }
-        tc_mma_tf32_ts_elect(td, fh, d_th + fo, idesc, single ? (unsigned)(ks != 0) : 1u);
-      }
-      mbar_wait(a_ready + s, ph);
-      tc_fence_after();
-      __syncwarp();
+      const unsigned long long d_th = d_t0 + (unsigned long long)(2 * s) * t2d, d_tl = d_th + t2d;
       const unsigned ab = tmem_base + TM_A + (unsigned)(s * 2 * KA);
-#pragma unroll 1
-      for (int ks = 0; ks < KA / 8; ++ks) {
+      L2WAIT_HOT(d_free + s, ph ^ 1u);
+      L2WAIT_HOT(b_ready + s, ph);
+      L2TR(6, it);
+      tc_fence_after();
+      __syncwarp();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (ks < nkq && !L2DBG(4)) {
+          const unsigned long long fo = (unsigned long long)(ks * 16);
+          const unsigned fh = tmem_base + TM_FHI + 8u * ks, fl = tmem_base + TM_FLO + 8u * ks;
+          if (!single) {
+            tc_mma_tf32_ts_elect(td, fl, d_th + fo, idesc, ks != 0);
+            tc_mma_tf32_ts_elect(td, fh, d_tl + fo, idesc, 1u);
+          }
+          tc_mma_tf32_ts_elect(td, fh, d_th + fo, idesc, single ? (unsigned)(ks != 0) : 1u);
+        }
+      }
+      L2WAIT_HOT(a_ready + s, ph);
+      L2TR(7, it);
+      tc_fence_after();
+      __syncwarp();
+#pragma unroll
+      for (int ks = 0; ks < (L2DBG(4) ? 0 : KA / 8); ++ks) {
         const unsigned long long fo = (unsigned long long)(ks * 16);
         const unsigned ah = ab + 8u * ks, al = ah + KA;
         if (!single) {
@@ -358,148 +457,138 @@ layer2d_tc_kernel(const L2Args p) {
         tc_mma_tf32_ts_elect(td, ah, d_wh + fo, idesc, 1u);
       }
       tc_commit_elect(mma_done + s);
+      L2TR(8, it);
     }
-  } else if (warp == Cfg::BPREP_WARP) {
-    // ---- T2 operand tile: global (fp32, operand layout) -> hi / lo in shared memory ----------------------
-    constexpr int NF = Cfg::F4_PER_LANE;
-    const int NG = (C + 7) >> 3;
-    const int nf4 = NG * KQ * 2;                      // float4 per tile
+  } else if (warp >= Cfg::BPREP_WARP0) {
+    // ---- T2 operand tiles: warp j owns the rows of parity j, i.e. operand buffer s = j and ring slots j, j + 2.
+    // lane 0 bulk-copies the raw tile (2.3 KB at cfg 1) into the ring two own rows ahead; the warp splits it hi / lo
+    // into the operand buffer.  These warps have no global traffic of their own in flight, so the proxy fence their
+    // shared-memory stores need (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) is cheap here.
+    constexpr int NFB = Cfg::NFB;
+    const int j = warp - Cfg::BPREP_WARP0, s = j;
+    const int tile_f4 = p.tile_floats >> 2;
+    const float4* __restrict__ ring4 = reinterpret_cast<const float4*>(ring) + lane;
+    float4* __restrict__ dh = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s) * t2_tile) + lane;
+    float4* __restrict__ dl = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s + 1) * t2_tile) + lane;
     const unsigned tile_bytes = (unsigned)p.tile_floats * 4u;
-    auto issue = [&](int it) {                        // lane 0: one bulk copy per tile
+    auto issue = [&](int it) {                          // one bulk copy per raw T2 tile into the ring
       const int slot = it & (L2_NR - 1);
       mbar_arrive_expect_tx(raw_full + slot, tile_bytes);
       bulk_g2s(ring + (size_t)slot * p.tile_floats, p.T2g + (size_t)(t_begin + it) * p.tile_floats, tile_bytes, raw_full + slot);
     };
-    if (lane == 0)
-      for (int i = 0; i < L2_NR && i < ntl; ++i) issue(i);
+    if (lane == 0) {
+      if (j < ntl) issue(j);
+      if (j + 2 < ntl) issue(j + 2);
+    }
     __syncwarp();
-    for (int it = 0; it < ntl; ++it) {
-      const int s = it & 1;
+    for (int it = j; it < ntl; it += 2) {
       const unsigned ph = ((unsigned)it >> 1) & 1u;
       const int slot = it & (L2_NR - 1);
-      mbar_wait(raw_full + slot, ((unsigned)it / L2_NR) & 1u);
-      float4 raw[NF];
-      const float4* __restrict__ src = reinterpret_cast<const float4*>(ring + (size_t)slot * p.tile_floats);
+      L2WAIT_COLD(raw_full + slot, ((unsigned)it / L2_NR) & 1u);
+      if (j == 0) L2TR(12, it);
+      float4 raw[NFB];
 #pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        const int f = lane + 32 * i;
-        raw[i] = (f < nf4) ? src[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int i = 0; i < NFB; ++i)
+        if (lane + 32 * i < tile_f4) raw[i] = ring4[(size_t)slot * tile_f4 + 32 * i];
       __syncwarp();
       if (lane == 0 && it + L2_NR < ntl) issue(it + L2_NR);          // the slot has been read: refill it
-      mbar_wait(mma_done + s, ph ^ 1u);
-      if (r_edge > 0) mbar_wait(edge_done + s, ph ^ 1u);
-      float4* __restrict__ dh = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s) * t2_tile);
-      float4* __restrict__ dl = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s + 1) * t2_tile);
+      L2WAIT_COLD(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read B buffer s
+      if (j == 0) L2TR(13, it);
 #pragma unroll
-      for (int i = 0; i < NF; ++i) {
-        const int f = lane + 32 * i;
-        if (f < nf4) {
-          // float4 f of the tile: row group g, chunk kc, row r  ->  n = 8 g + r, k = 4 kc .. 4 kc + 3
-          const int g = f / (KQ * 2), rem = f - g * KQ * 2;
-          const int kc = rem >> 3, n = 8 * g + (rem & 7);
-          const float in[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
-          float hi[4], lo[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float v = (n < C && 4 * kc + e < m2x2) ? in[e] : 0.f;
-            split_tf32(v, hi[e], lo[e]);
-          }
-          dh[f] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          dl[f] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      for (int i = 0; i < NFB; ++i) {
+        if (lane + 32 * i < tile_f4) {
+          float4 hi, lo;
+          split_tf32(raw[i].x, hi.x, lo.x); split_tf32(raw[i].y, hi.y, lo.y);
+          split_tf32(raw[i].z, hi.z, lo.z); split_tf32(raw[i].w, hi.w, lo.w);
+          dh[32 * i] = hi;
+          dl[32 * i] = lo;
         }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(b_ready + s);
+      if (j == 0) L2TR(14, it);
     }
-  } else {
-    // ---- edge warp: the W - 128 columns that do not fit the TMEM lanes, on the FP32 pipes ------------------
-    constexpr int ECH = Cfg::ECH;
-    float pa[L2_EPF][ECH][L2_RMAX];
-    auto load_tile = [&](int it, float (&r)[ECH][L2_RMAX]) {
-      if (it >= ntl || r_edge == 0) return;
-      const long T = t_begin + it;
-      const unsigned b = p.rs_div.div((unsigned)T);
-      const unsigned row = (unsigned)T - b * (unsigned)p.RS;
+  } else if (r_edge > 0 && !L2DBG(8)) {
+    // ---- edge warp: the W - 128 columns that do not fit the TMEM lanes, on the FP32 pipes.  lane = row: 32 rows
+    // per pass, each lane reads its row's T2 tile (L2) and edge activations, weights / twiddles are broadcasts
+    const float* __restrict__ abase = p.a + Wm;
+    float* __restrict__ obase = p.out + Wm;
+    float* __restrict__ sbase = SOUT ? p.s_out + Wm : nullptr;
+    const bool pair_ok = ((W & 1) == 0) && ((reinterpret_cast<size_t>(p.a) & 7) == 0);
+    for (int base = 0; base < ntl; base += 32) {
+      const bool live = base + lane < ntl;
+      const unsigned T = (unsigned)(t_begin + (live ? base + lane : ntl - 1));
+      const unsigned b = rsd.div(T);
+      const unsigned row = T - b * RS;
+      const size_t roff = (size_t)b * bs + (size_t)row * W;
+      const float4* __restrict__ trow = reinterpret_cast<const float4*>(p.T2g + (size_t)T * p.tile_floats);
+      for (int j0 = 0; j0 < r_edge; j0 += 2) {             // two edge columns per pass
+        const bool two = j0 + 1 < r_edge;
+        const float* __restrict__ arow = abase + roff + j0;
+        auto lda = [&](int ci) -> float2 {
+          const float* __restrict__ q = arow + (size_t)ci * cs;
+          if (two && pair_ok) return __ldg(reinterpret_cast<const float2*>(q));
+          return make_float2(__ldg(q), two ? __ldg(q + 1) : 0.f);
+        };
+        float2 av[CX > 0 ? CX : 1];
+        if (CX > 0) {
 #pragma unroll
-      for (int ch = 0; ch < ECH; ++ch) {
-        const int ci = lane + 32 * ch;
-        const float* __restrict__ src = p.a + (((size_t)b * C + ci) * p.RS + row) * W + Wm;
+          for (int ci = 0; ci < (CX > 0 ? CX : 1); ++ci) av[ci] = lda(ci);
+        }
+        const float4* __restrict__ f0 = reinterpret_cast<const float4*>(eF + j0 * KQ);
+        const float4* __restrict__ f1 = reinterpret_cast<const float4*>(eF + (j0 + 1) * KQ);
+#pragma unroll 1
+        for (int co = 0; co < C; ++co) {
+          const float4* __restrict__ tp = trow + (co >> 3) * KQ * 2 + (co & 7);
+          float4 t[8];
 #pragma unroll
-        for (int j = 0; j < L2_RMAX; ++j) r[ch][j] = (ci < C && j < r_edge) ? __ldg(src + j) : 0.f;
-      }
-    };
-    auto do_tile = [&](int it, float (&r)[ECH][L2_RMAX]) {
-      const int s = it & 1;
-      const unsigned ph = ((unsigned)it >> 1) & 1u;
-      const long T = t_begin + it;
-      const unsigned b = p.rs_div.div((unsigned)T);
-      const unsigned row = (unsigned)T - b * (unsigned)p.RS;
+          for (int kc = 0; kc < 8; ++kc)
+            if (kc < KQ / 4) t[kc] = __ldg(tp + kc * 8);
+          float acc0 = eB[co], acc1 = acc0;
 #pragma unroll
-      for (int ch = 0; ch < ECH; ++ch) {
-        const int ci = lane + 32 * ch;
-        if (ci < C) *reinterpret_cast<float4*>(eA + ci * L2_RMAX) = make_float4(r[ch][0], r[ch][1], r[ch][2], r[ch][3]);
-      }
-      __syncwarp();
-      mbar_wait(b_ready + s, ph);
-      const float* __restrict__ th = bT2 + (size_t)(2 * s) * t2_tile;
-      const float* __restrict__ tl = th + t2_tile;
+          for (int kc = 0; kc < 8; ++kc) {
+            if (kc < KQ / 4) {
+              const float4 fa = f0[kc], fb = f1[kc];
+              acc0 = fmaf(t[kc].x, fa.x, acc0); acc1 = fmaf(t[kc].x, fb.x, acc1);
+              acc0 = fmaf(t[kc].y, fa.y, acc0); acc1 = fmaf(t[kc].y, fb.y, acc1);
+              acc0 = fmaf(t[kc].z, fa.z, acc0); acc1 = fmaf(t[kc].z, fb.z, acc1);
+              acc0 = fmaf(t[kc].w, fa.w, acc0); acc1 = fmaf(t[kc].w, fb.w, acc1);
+            }
+          }
+          const float4* __restrict__ w4 = reinterpret_cast<const float4*>(eW + co * CP);
+          if (CX > 0) {
 #pragma unroll
-      for (int ch = 0; ch < ECH; ++ch) {
-        const int co = lane + 32 * ch;
-        if (co < C) {
-          const int ro = (co >> 3) * KQ * 8 + (co & 7) * 4;
-          const size_t off = (((size_t)b * C + co) * p.RS + row) * W + Wm;
-          for (int j0 = 0; j0 < r_edge; j0 += 2) {             // two edge columns per pass
-            float acc0 = eB[co], acc1 = acc0;
-            const float* __restrict__ f0 = eF + j0 * KQ;
-            const float* __restrict__ f1 = f0 + KQ;
+            for (int c4 = 0; c4 < (CX + 3) / 4; ++c4) {
+              const float4 wq = w4[c4];
+              const float wj[4] = {wq.x, wq.y, wq.z, wq.w};
 #pragma unroll
-            for (int kc = 0; kc < 8; ++kc) {
-              if (kc < KQ / 4) {
-                const float4 h4 = *reinterpret_cast<const float4*>(th + ro + kc * 32);
-                const float4 l4 = *reinterpret_cast<const float4*>(tl + ro + kc * 32);
-                const float t0 = h4.x + l4.x, t1 = h4.y + l4.y, t2 = h4.z + l4.z, t3 = h4.w + l4.w;   // = the fp32 value
-                const float4 fa = *reinterpret_cast<const float4*>(f0 + kc * 4);
-                const float4 fb = *reinterpret_cast<const float4*>(f1 + kc * 4);
-                acc0 = fmaf(t0, fa.x, acc0); acc1 = fmaf(t0, fb.x, acc1);
-                acc0 = fmaf(t1, fa.y, acc0); acc1 = fmaf(t1, fb.y, acc1);
-                acc0 = fmaf(t2, fa.z, acc0); acc1 = fmaf(t2, fb.z, acc1);
-                acc0 = fmaf(t3, fa.w, acc0); acc1 = fmaf(t3, fb.w, acc1);
+              for (int e = 0; e < 4; ++e) {
+                if (4 * c4 + e < CX) {
+                  acc0 = fmaf(wj[e], av[4 * c4 + e].x, acc0);
+                  acc1 = fmaf(wj[e], av[4 * c4 + e].y, acc1);
+                }
               }
             }
-#pragma unroll 4
+          } else {
             for (int ci = 0; ci < C; ++ci) {
-              const float wv = eW[co * (C + 1) + ci];
-              const float2 av = *reinterpret_cast<const float2*>(eA + ci * L2_RMAX + j0);
-              acc0 = fmaf(wv, av.x, acc0);
-              acc1 = fmaf(wv, av.y, acc1);
+              const float wj = eW[co * CP + ci];
+              const float2 a2 = lda(ci);
+              acc0 = fmaf(wj, a2.x, acc0);
+              acc1 = fmaf(wj, a2.y, acc1);
             }
-            if (p.s_out != nullptr) {
-              p.s_out[off + j0] = acc0;
-              if (j0 + 1 < r_edge) p.s_out[off + j0 + 1] = acc1;
+          }
+          if (live) {
+            const size_t off = roff + (size_t)co * cs + j0;
+            if (SOUT) {
+              sbase[off] = acc0;
+              if (two) sbase[off + 1] = acc1;
             }
-            p.out[off + j0] = p.apply_gelu ? gelu_fast(acc0) : acc0;
-            if (j0 + 1 < r_edge) p.out[off + j0 + 1] = p.apply_gelu ? gelu_fast(acc1) : acc1;
+            obase[off] = GELU ? gelu_fast(acc0) : acc0;
+            if (two) obase[off + 1] = GELU ? gelu_fast(acc1) : acc1;
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(edge_done + s);
-    };
-    if (r_edge > 0) {
-#pragma unroll
-    for (int d = 0; d < L2_EPF; ++d) load_tile(d, pa[d]);
-    for (int it = 0; it < ntl; it += L2_EPF) {
-#pragma unroll
-      for (int d = 0; d < L2_EPF; ++d) {
-        if (it + d < ntl) {
-          do_tile(it + d, pa[d]);
-          load_tile(it + d + L2_EPF, pa[d]);
-        }
-      }
-    }
     }
   }
   tc_fence_before();
@@ -509,19 +598,29 @@ layer2d_tc_kernel(const L2Args p) {
 
 template <int KA, int NPAD, int CWQ>
 size_t layer2d_smem_bytes(int KQ, int C) {
-  return sizeof(float) * ((size_t)4 * NPAD * KQ + 2 * NPAD * KA + (size_t)((C * (C + 1) + 3) & ~3) + NPAD + L2_RMAX * KQ +
-                          NPAD * L2_RMAX + (size_t)L2_NR * ((C + 7) / 8) * KQ * 8) + 16 + (10 + L2_NR) * 8 + 16;
+  const size_t CP = (size_t)((C + 3) & ~3);
+  return sizeof(float) * ((size_t)4 * NPAD * KQ + 2 * NPAD * KA + (size_t)C * CP + NPAD + L2_RMAX * KQ +
+                          (size_t)L2_NR * ((C + 7) / 8) * KQ * 8) + 16 + (9 + L2_NR) * 8 + 16;
 }
 
-template <int KA, int NPAD, int CWQ>
-int launch_layer2d_t(const L2Args& args, cudaStream_t st) {
+template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT>
+int launch_layer2d_k(const L2Args& args, cudaStream_t st) {
   using Cfg = L2Cfg<KA, NPAD, CWQ>;
   const size_t smem = layer2d_smem_bytes<KA, NPAD, CWQ>(args.KQ, args.C);
   if (smem > 48 * 1024) { set_error("layer2d_tc: shared memory %zu", smem); return FNO_E_ARG; }
   const long ctas = args.total_tiles < 148 ? args.total_tiles : 148;
-  layer2d_tc_kernel<KA, NPAD, CWQ><<<(unsigned)ctas, Cfg::THREADS, smem, st>>>(args);
+  layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT><<<(unsigned)ctas, Cfg::THREADS, smem, st>>>(args);
   count_launch();
   return check_launch("layer2d_tc_kernel");
+}
+
+template <int KA, int NPAD, int CWQ, int CX>
+int launch_layer2d_t(const L2Args& args, cudaStream_t st) {
+  const bool so = args.s_out != nullptr;
+  if (args.apply_gelu) return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st)
+                                 : launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st);
+  return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st)
+            : launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st);
 }
 
 template <int M1T>
@@ -590,12 +689,41 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
   args.transpose_w = transpose_w; args.apply_gelu = apply_gelu;
   args.single = g_math_mode.load() == FNO_MATH_TF32;
   args.rs_div.init((unsigned)args.RS);
+  args.trace = nullptr;
+  args.dbg = 0;
+#ifdef L2_TRACE
+  static unsigned long long* trace_buf = nullptr;
+  const bool tracing = std::getenv("FNO_L2_TRACE") != nullptr;
+  { const char* e = std::getenv("FNO_L2_DBG"); args.dbg = e ? std::atoi(e) : 0; }
+  if (tracing && trace_buf == nullptr) cudaMalloc(&trace_buf, 64 * 16 * 8);
+  if (tracing) { cudaMemset(trace_buf, 0, 64 * 16 * 8); args.trace = trace_buf; }
+#endif
+
   const int KA = (C + 1 + 7) & ~7;
+  if (C == 20) {                                                     // the reference's width: channel loops unrolled
+    rc = launch_layer2d_t<24, 32, 2, 20>(args, st);
+#ifdef L2_TRACE
+    static int calls = 0;
+    if (args.trace != nullptr && ++calls == 5) {
+      unsigned long long h[64 * 16];
+      cudaDeviceSynchronize();
+      cudaMemcpy(h, args.trace, sizeof(h), cudaMemcpyDeviceToHost);
+      const unsigned long long t0 = h[20 * 16 + 6];
+      fprintf(stderr, "ev: 0 conv-wake 1 fenced 2 loads-in 3 sttm-issued 4 - 5 arrived | 6 mma-bready 7 mma-aready 8 committed | 9 epi-wake 10 epi-ld 11 epi-end | 12 bp-raw 13 bp-free 14 bp-arrived\n");
+      for (int it = 20; it < 32; ++it) {
+        fprintf(stderr, "tile %2d:", it);
+        for (int e = 0; e < 15; ++e) fprintf(stderr, " %6lld", h[it * 16 + e] ? (long long)(h[it * 16 + e] - t0) : -1LL);
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
+    return rc;
+  }
   switch (KA) {
-    case 8: return launch_layer2d_t<8, 32, 2>(args, st);
-    case 16: return launch_layer2d_t<16, 32, 2>(args, st);
-    case 24: return launch_layer2d_t<24, 32, 2>(args, st);
-    case 32: return launch_layer2d_t<32, 32, 2>(args, st);
+    case 8: return launch_layer2d_t<8, 32, 2, 0>(args, st);
+    case 16: return launch_layer2d_t<16, 32, 2, 0>(args, st);
+    case 24: return launch_layer2d_t<24, 32, 2, 0>(args, st);
+    case 32: return launch_layer2d_t<32, 32, 2, 0>(args, st);
     default: set_error("layer2d_tc: width %d unsupported", C); return FNO_E_ARG;
   }
 }
