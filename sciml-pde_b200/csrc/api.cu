@@ -189,6 +189,7 @@ int create_common(int device, int nd, int D1, int H, int W, int m1x, int m1, int
   }
   if (rc == FNO_OK) rc = setup_transform2d_attrs(p);
   if (rc == FNO_OK) rc = build_tc_tables(p);
+  if (rc == FNO_OK) rc = setup_layer2d_tc_attrs();
   cudaSetDevice(cur);
   if (rc != FNO_OK) { free_plan(p); return rc; }
   {

@@ -58,6 +58,7 @@ int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cuda
 int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
                     cudaStream_t st, bool attr_only);
 bool layer2d_tc_supported(const Plan* p, int C);
+int setup_layer2d_tc_attrs();
 size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C);
 int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float* Wl, const float* bias, float* s_out,
                       float* out, float* work, int B, int C, int cmode, float scale, int apply_gelu, int transpose_w,

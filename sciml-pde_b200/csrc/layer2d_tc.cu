@@ -50,7 +50,7 @@ namespace {
 #endif
 constexpr int L2_RMAX = 4;        // edge columns (W - 128) handled on the FP32 pipes
 constexpr int L2_NR = 4;          // T2 tiles in flight (bulk copies into a shared-memory ring)
-constexpr int L2_PD = 2;          // own rows of activation loads in flight per converter thread (= 4 rows ahead)
+constexpr int L2_PD = 3;          // own rows of activation copies in flight per converter warp (= 6 rows ahead)
 
 __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -139,6 +139,65 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
 }
 
 // ------------------------------------------------------------------------------------------------------
+// spectral part of the edge columns w = Wm + j (j < RE) that do not fit the 128 TMEM lanes:
+//   E[plane, h, j] = Re sum_{r, q} sc_q Y[r, q] e^{+2 pi i (k_r h / H + q w_j / W)}
+// contiguous axis first (U[r, j] = sum_q sc_q Y[r, q] e^{i phi_q w_j}, 2 m1 x RE complex numbers per plane, shared
+// memory), then the strided axis per row.  0.1 % of the layer's flops; the main kernel's edge warp adds the bypass.
+// ------------------------------------------------------------------------------------------------------
+constexpr int HE_PB = 8;      // planes per block
+template <int M1T>
+__global__ void __launch_bounds__(256)
+hinv_edge_kernel(const float2* __restrict__ Y, float* __restrict__ E, const float* __restrict__ twH,
+                 const float* __restrict__ twW, int H, int W, int WP, int Wm, int RE, int r_edge, int m1, int m2, long planes,
+                 int cmode, float scale) {
+  constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
+  __shared__ float2 U[HE_PB][2 * M1T][L2_RMAX];
+  const long p0 = (long)blockIdx.x * HE_PB;
+  const int R = 2 * m1;
+  for (int i = threadIdx.x; i < HE_PB * R * RE; i += blockDim.x) {
+    const int j = i % RE, r = (i / RE) % R, pl = i / (RE * R);
+    float2 acc = make_float2(0.f, 0.f);
+    if (p0 + pl < planes && j < r_edge) {
+      const float2* __restrict__ yp = Y + ((size_t)(p0 + pl) * R + r) * m2;
+      for (int q = 0; q < m2; ++q) {
+        float sc = scale;
+        if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
+        const float2 y = __ldg(yp + q);
+        const float c = sc * __ldg(twW + (size_t)q * WP + Wm + j), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + Wm + j);
+        acc.x = fmaf(y.x, c, acc.x); acc.x = fmaf(-y.y, sn, acc.x);
+        acc.y = fmaf(y.x, sn, acc.y); acc.y = fmaf(y.y, c, acc.y);
+      }
+    }
+    U[pl][r][j] = acc;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HE_PB * H; i += blockDim.x) {
+    const int h = i % H, pl = i / H;
+    if (p0 + pl >= planes) break;
+    const int t = (2 * h <= H) ? h : H - h;
+    const float sg = (2 * h <= H) ? 1.0f : -1.0f;
+    const float* __restrict__ tw = twH + (size_t)t * JP;
+    float e[L2_RMAX];
+#pragma unroll
+    for (int j = 0; j < L2_RMAX; ++j) e[j] = U[pl][0][j].x;          // k = 0
+    for (int jj = 1; jj <= m1; ++jj) {
+      const float c = __ldg(tw + jj), sn = sg * __ldg(tw + M1T + jj);
+#pragma unroll
+      for (int j = 0; j < L2_RMAX; ++j) {
+        if (jj < m1) {                                                // k = +jj (row jj)
+          const float2 u = U[pl][jj][j];
+          e[j] = fmaf(u.x, c, e[j]); e[j] = fmaf(-u.y, sn, e[j]);
+        }
+        const float2 v = U[pl][R - jj][j];                            // k = -jj (row 2 m1 - jj)
+        e[j] = fmaf(v.x, c, e[j]); e[j] = fmaf(v.y, sn, e[j]);
+      }
+    }
+    float* __restrict__ o = E + ((size_t)(p0 + pl) * H + h) * RE;
+    for (int j = 0; j < RE; ++j) o[j] = e[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------------------
 template <int KA, int NPAD, int CWQ>
@@ -160,6 +219,8 @@ struct L2Cfg {
 struct L2Args {
   const float* a;       // [B, C, RS, W] activation (forward) / dS (adjoint)
   const float* T2g;     // [B * RS] tiles from hinv_tiles_kernel
+  const float* E;       // [B * C * RS][RE] spectral part of the edge columns (hinv_edge_kernel)
+  int RE;
   const float* Wl;      // [C, C] bypass weight
   const float* bias;    // [C] or null
   float* s_out;         // optional pre-activation
@@ -202,8 +263,9 @@ layer2d_tc_kernel(const L2Args p) {
   float* eB = eW + C * CP;                                // [NPAD] bias
   float* eF = eB + NPAD;                                  // [L2_RMAX][KQ] twiddles of the edge columns
   float* ring = eF + L2_RMAX * KQ;                        // [L2_NR][tile_floats] raw T2 tiles (bulk-copy destination)
+  float* stage = ring + (size_t)L2_NR * p.tile_floats;    // [CONV_WARPS][L2_PD][KA][32] activation rows (cp.async)
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-      (reinterpret_cast<size_t>(ring + (size_t)L2_NR * p.tile_floats) + 15) & ~size_t(15));
+      (reinterpret_cast<size_t>(stage + (size_t)Cfg::CONV_WARPS * L2_PD * KA * 32) + 15) & ~size_t(15));
   unsigned long long* a_ready = bars;                  // [2] converters wrote A buffer s
   unsigned long long* mma_done = bars + 2;             // [2] MMAs of the tile on buffers s complete (A / B free, D full)
   unsigned long long* d_free = bars + 4;               // [2] accumulator s read back
@@ -296,38 +358,49 @@ layer2d_tc_kernel(const L2Args p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(f_ready);
     }
+    // activation staging: cp.async (LDGSTS) into a per-warp shared-memory ring, L2_PD own rows (2 L2_PD rows) ahead.
+    // Register prefetch does not work here: the loads of the row after next land on the same scoreboard as the ones
+    // about to be consumed, so the warp waited a full DRAM latency per row (ncu: long_scoreboard on the first use).
     constexpr int NLD = CX > 0 ? CX : KA - 1;                 // channel slots per thread (C <= KA - 1)
     const float* __restrict__ abase = p.a + w;
     const unsigned ah = ta + TM_A + (unsigned)(par * 2 * KA), al = ah + KA;
     const int s = par;
-    float pre[L2_PD][NLD];
-    auto load_tile = [&](int it, float (&r)[NLD]) {
-      if (it >= ntl) return;
-      const unsigned T = (unsigned)(t_begin + it);
-      const unsigned b = rsd.div(T);
-      const unsigned row = T - b * RS;
-      const float* __restrict__ src = abase + (size_t)b * bs + (size_t)row * W;
+    float* __restrict__ stg = stage + (size_t)warp * L2_PD * (KA * 32) + lane;      // [L2_PD][KA][32 lanes]
+    const unsigned stg_u32 = smem_u32(stg);
+    auto load_tile = [&](int it, int slot) {
+      if (it < ntl && wv && !L2DBG(2)) {
+        const unsigned T = (unsigned)(t_begin + it);
+        const unsigned b = rsd.div(T);
+        const unsigned row = T - b * RS;
+        const float* __restrict__ src = abase + (size_t)b * bs + (size_t)row * W;
+        const unsigned dst = stg_u32 + (unsigned)(slot * KA * 32 * 4);
 #pragma unroll
-      for (int i = 0; i < NLD; ++i) {
-        r[i] = (wv && i < C && !L2DBG(2)) ? __ldg(src) : 0.f;
-        src += cs;
+        for (int i = 0; i < NLD; ++i) {
+          if (i < C) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (unsigned)(i * 128)), "l"(src) : "memory");
+          src += cs;
+        }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto column = [&](const float (&r)[NLD], int col) -> float {      // col is a compile-time constant after unrolling
-      return col < NLD ? ((CX == 0 && col == C) ? 1.0f : r[col < NLD ? col : 0]) : (col == C ? 1.0f : 0.f);
-    };
-    auto convert_tile = [&](int it, float (&r)[NLD]) {
+    auto convert_tile = [&](int it, int slot) {
       const unsigned ph = ((unsigned)it >> 1) & 1u;
+      asm volatile("cp.async.wait_group %0;" ::"n"(L2_PD - 1) : "memory");          // this row's copies have landed
+      float r[NLD];
+      const float* __restrict__ sp = stg + (size_t)slot * (KA * 32);
+#pragma unroll
+      for (int i = 0; i < NLD; ++i) r[i] = (wv && i < C) ? sp[i * 32] : 0.f;
       L2WAIT_COLD(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read A buffer s
       if (warp == 0) L2TR(0, it);
       tc_fence_after();
-      if (warp == 0) L2TR(1, it);
+      auto column = [&](int col) -> float {         // col is a compile-time constant after unrolling
+        return col < NLD ? ((CX == 0 && col == C) ? 1.0f : r[col < NLD ? col : 0]) : (col == C ? 1.0f : 0.f);
+      };
 #pragma unroll
       for (int c0 = 0; c0 < KA; c0 += 16) {
         if (KA - c0 >= 16) {
           float hi[16], lo[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) split_tf32(column(r, c0 + e), hi[e], lo[e]);
+          for (int e = 0; e < 16; ++e) split_tf32(column(c0 + e), hi[e], lo[e]);
           if (!L2DBG(16)) {
             tmem_st16(ah + (unsigned)c0, hi);
             if (!single) tmem_st16(al + (unsigned)c0, lo);
@@ -335,7 +408,7 @@ layer2d_tc_kernel(const L2Args p) {
         } else {
           float hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_tf32(column(r, c0 + e), hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) split_tf32(column(c0 + e), hi[e], lo[e]);
           if (!L2DBG(16)) {
             tmem_st8(ah + (unsigned)c0, hi);
             if (!single) tmem_st8(al + (unsigned)c0, lo);
@@ -344,21 +417,18 @@ layer2d_tc_kernel(const L2Args p) {
       }
       if (warp == 0) L2TR(3, it);
       tmem_st_wait();                              // (no fence.proxy.async here: it compiles to MEMBAR.ALL.CTA, which would
-      tc_fence_before();                           //  wait for this warp's prefetched global loads every tile)
+      tc_fence_before();                           //  wait for this warp's copies in flight every row)
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + s);
       if (warp == 0) L2TR(5, it);
     };
 #pragma unroll
-    for (int d = 0; d < L2_PD; ++d) load_tile(par + 2 * d, pre[d]);
-    for (int it = par; it < ntl; it += 2 * L2_PD) {
-#pragma unroll
-      for (int d = 0; d < L2_PD; ++d) {
-        if (it + 2 * d < ntl) {
-          convert_tile(it + 2 * d, pre[d]);
-          load_tile(it + 2 * d + 2 * L2_PD, pre[d]);
-        }
-      }
+    for (int d = 0; d < L2_PD; ++d) load_tile(par + 2 * d, d);
+    int slot = 0;
+    for (int it = par; it < ntl; it += 2) {
+      convert_tile(it, slot);
+      load_tile(it + 2 * L2_PD, slot);
+      slot = (slot + 1 == L2_PD) ? 0 : slot + 1;
     }
   } else if (warp < Cfg::MMA_WARP) {
     // ---- epilogue: thread = w, a slice of the output channels ------------------------------------------
@@ -510,11 +580,13 @@ layer2d_tc_kernel(const L2Args p) {
       if (j == 0) L2TR(14, it);
     }
   } else if (r_edge > 0 && !L2DBG(8)) {
-    // ---- edge warp: the W - 128 columns that do not fit the TMEM lanes, on the FP32 pipes.  lane = row: 32 rows
-    // per pass, each lane reads its row's T2 tile (L2) and edge activations, weights / twiddles are broadcasts
+    // ---- edge warp: the W - 128 columns that do not fit the TMEM lanes, on the FP32 pipes, independent of the
+    // pipeline.  lane = row, 32 rows per pass: spectral part from hinv_edge_kernel (coalesced over the rows), bypass
+    // = C x C FMAs per column with the weights as shared-memory broadcasts; all loads of a pass are issued up front.
     const float* __restrict__ abase = p.a + Wm;
     float* __restrict__ obase = p.out + Wm;
     float* __restrict__ sbase = SOUT ? p.s_out + Wm : nullptr;
+    const int RE = p.RE;
     const bool pair_ok = ((W & 1) == 0) && ((reinterpret_cast<size_t>(p.a) & 7) == 0);
     for (int base = 0; base < ntl; base += 32) {
       const bool live = base + lane < ntl;
@@ -522,7 +594,7 @@ layer2d_tc_kernel(const L2Args p) {
       const unsigned b = rsd.div(T);
       const unsigned row = T - b * RS;
       const size_t roff = (size_t)b * bs + (size_t)row * W;
-      const float4* __restrict__ trow = reinterpret_cast<const float4*>(p.T2g + (size_t)T * p.tile_floats);
+      const float* __restrict__ erow = p.E + ((size_t)b * C * RS + row) * RE;       // + co * RS * RE
       for (int j0 = 0; j0 < r_edge; j0 += 2) {             // two edge columns per pass
         const bool two = j0 + 1 < r_edge;
         const float* __restrict__ arow = abase + roff + j0;
@@ -536,26 +608,10 @@ layer2d_tc_kernel(const L2Args p) {
 #pragma unroll
           for (int ci = 0; ci < (CX > 0 ? CX : 1); ++ci) av[ci] = lda(ci);
         }
-        const float4* __restrict__ f0 = reinterpret_cast<const float4*>(eF + j0 * KQ);
-        const float4* __restrict__ f1 = reinterpret_cast<const float4*>(eF + (j0 + 1) * KQ);
-#pragma unroll 1
+#pragma unroll 4
         for (int co = 0; co < C; ++co) {
-          const float4* __restrict__ tp = trow + (co >> 3) * KQ * 2 + (co & 7);
-          float4 t[8];
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc)
-            if (kc < KQ / 4) t[kc] = __ldg(tp + kc * 8);
-          float acc0 = eB[co], acc1 = acc0;
-#pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
-            if (kc < KQ / 4) {
-              const float4 fa = f0[kc], fb = f1[kc];
-              acc0 = fmaf(t[kc].x, fa.x, acc0); acc1 = fmaf(t[kc].x, fb.x, acc1);
-              acc0 = fmaf(t[kc].y, fa.y, acc0); acc1 = fmaf(t[kc].y, fb.y, acc1);
-              acc0 = fmaf(t[kc].z, fa.z, acc0); acc1 = fmaf(t[kc].z, fb.z, acc1);
-              acc0 = fmaf(t[kc].w, fa.w, acc0); acc1 = fmaf(t[kc].w, fb.w, acc1);
-            }
-          }
+          const float2 e2 = __ldg(reinterpret_cast<const float2*>(erow + (size_t)co * RS * RE + j0));
+          float acc0 = eB[co] + e2.x, acc1 = eB[co] + e2.y;
           const float4* __restrict__ w4 = reinterpret_cast<const float4*>(eW + co * CP);
           if (CX > 0) {
 #pragma unroll
@@ -600,14 +656,20 @@ template <int KA, int NPAD, int CWQ>
 size_t layer2d_smem_bytes(int KQ, int C) {
   const size_t CP = (size_t)((C + 3) & ~3);
   return sizeof(float) * ((size_t)4 * NPAD * KQ + 2 * NPAD * KA + (size_t)C * CP + NPAD + L2_RMAX * KQ +
-                          (size_t)L2_NR * ((C + 7) / 8) * KQ * 8) + 16 + (9 + L2_NR) * 8 + 16;
+                          (size_t)L2_NR * ((C + 7) / 8) * KQ * 8 + (size_t)8 * L2_PD * KA * 32) + 16 + (9 + L2_NR) * 8 + 16;
 }
 
 template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT>
-int launch_layer2d_k(const L2Args& args, cudaStream_t st) {
+int launch_layer2d_k(const L2Args& args, cudaStream_t st, bool attr_only) {
   using Cfg = L2Cfg<KA, NPAD, CWQ>;
   const size_t smem = layer2d_smem_bytes<KA, NPAD, CWQ>(args.KQ, args.C);
-  if (smem > 48 * 1024) { set_error("layer2d_tc: shared memory %zu", smem); return FNO_E_ARG; }
+  if (smem > 200 * 1024) { set_error("layer2d_tc: shared memory %zu", smem); return FNO_E_ARG; }
+  if (attr_only) {
+    if (cudaFuncSetAttribute(layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             200 * 1024) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(layer2d_tc)");
+    return FNO_OK;
+  }
   const long ctas = args.total_tiles < 148 ? args.total_tiles : 148;
   layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT><<<(unsigned)ctas, Cfg::THREADS, smem, st>>>(args);
   count_launch();
@@ -615,12 +677,19 @@ int launch_layer2d_k(const L2Args& args, cudaStream_t st) {
 }
 
 template <int KA, int NPAD, int CWQ, int CX>
-int launch_layer2d_t(const L2Args& args, cudaStream_t st) {
+int launch_layer2d_t(const L2Args& args, cudaStream_t st, bool attr_only = false) {
+  if (attr_only) {                         // once per device: raise the dynamic shared-memory limit of all four forms
+    int rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st, true);
+    return rc;
+  }
   const bool so = args.s_out != nullptr;
-  if (args.apply_gelu) return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st)
-                                 : launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st);
-  return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st)
-            : launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st);
+  if (args.apply_gelu) return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st, false)
+                                 : launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st, false);
+  return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st, false)
+            : launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st, false);
 }
 
 template <int M1T>
@@ -654,12 +723,37 @@ bool layer2d_tc_supported(const Plan* p, int C) {
   return true;
 }
 
+// raises the dynamic shared-memory limit of every instantiation on the CURRENT device (called from plan creation, which
+// has made the plan's device current: the attribute is per device, so a process-wide "done" flag would be wrong)
+int setup_layer2d_tc_attrs() {
+  L2Args args{};
+  args.KQ = 8; args.C = 1;
+  int rc = launch_layer2d_t<24, 32, 2, 20>(args, nullptr, true);
+  if (rc == FNO_OK) rc = launch_layer2d_t<8, 32, 2, 0>(args, nullptr, true);
+  if (rc == FNO_OK) rc = launch_layer2d_t<16, 32, 2, 0>(args, nullptr, true);
+  if (rc == FNO_OK) rc = launch_layer2d_t<24, 32, 2, 0>(args, nullptr, true);
+  if (rc == FNO_OK) rc = launch_layer2d_t<32, 32, 2, 0>(args, nullptr, true);
+  return rc;
+}
+
 static int kq_of(const Plan* p) { return (2 * p->m2 + 7) & ~7; }
 static int tile_floats_of(const Plan* p, int C) { return ((C + 7) / 8) * kq_of(p) * 8; }
 
+static int re_of(const Plan* p) { const int r = p->W > 128 ? p->W - 128 : 0; return (r + 1) & ~1; }
+
 size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C) {
   if (!layer2d_tc_supported(p, C) || B <= 0) return 0;
-  return sizeof(float) * (size_t)B * p->D1 * p->H * tile_floats_of(p, C);
+  return sizeof(float) * ((size_t)B * p->D1 * p->H * tile_floats_of(p, C) + (size_t)B * C * p->D1 * p->H * re_of(p));
+}
+
+template <int M1T>
+int launch_hinv_edge_t(const Plan* p, const float* Y, float* E, long planes, int cmode, float scale, cudaStream_t st) {
+  const int Wm = p->W < 128 ? p->W : 128;
+  const unsigned grid = (unsigned)((planes + HE_PB - 1) / HE_PB);
+  hinv_edge_kernel<M1T><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(Y), E, p->twH, p->twW, p->H, p->W, p->WP, Wm,
+                                              re_of(p), p->W - Wm, p->m1, p->m2, planes, cmode, scale);
+  count_launch();
+  return check_launch("hinv_edge_kernel");
 }
 
 // out = act( K3(Y) + Wl a + bias ),  s_out = pre-activation (optional);  transpose_w: Wl^T a (adjoint)
@@ -682,7 +776,21 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
     default: set_error("unsupported padded modes1 %d", p->M1T); return FNO_E_ARG;
   }
   if (rc != FNO_OK) return rc;
+  float* E = work + (size_t)total * tile_floats;             // 8-byte aligned: tile_floats is a multiple of 64
+  if (p->W > 128) {
+    const long planes = (long)B * C * p->D1;
+    switch (p->M1T) {
+      case 4: rc = launch_hinv_edge_t<4>(p, Y, E, planes, cmode, scale, st); break;
+      case 8: rc = launch_hinv_edge_t<8>(p, Y, E, planes, cmode, scale, st); break;
+      case 12: rc = launch_hinv_edge_t<12>(p, Y, E, planes, cmode, scale, st); break;
+      case 16: rc = launch_hinv_edge_t<16>(p, Y, E, planes, cmode, scale, st); break;
+      case 24: rc = launch_hinv_edge_t<24>(p, Y, E, planes, cmode, scale, st); break;
+      default: rc = launch_hinv_edge_t<32>(p, Y, E, planes, cmode, scale, st); break;
+    }
+    if (rc != FNO_OK) return rc;
+  }
   L2Args args;
+  args.E = E; args.RE = re_of(p);
   args.a = a; args.T2g = work; args.Wl = Wl; args.bias = bias; args.s_out = s_out; args.out = out;
   args.twW = p->twW; args.WP = p->WP; args.W = p->W; args.m2 = p->m2; args.KQ = KQ; args.C = C;
   args.RS = p->D1 * p->H; args.tile_floats = tile_floats; args.total_tiles = total;
