@@ -30,7 +30,10 @@
 //                    tcgen05.st, 2 own rows of loads in flight
 //   MMA warp         18 tcgen05.mma per row into a double-buffered accumulator         b_ready, a_ready, d_free -> mma_done
 //   8 epilogue warps tcgen05.ld, GELU, stores                                          mma_done -> d_free
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "tc_common.cuh"
 
@@ -50,7 +53,21 @@ namespace {
 #endif
 constexpr int L2_RMAX = 4;        // edge columns (W - 128) handled on the FP32 pipes
 constexpr int L2_NR = 4;          // T2 tiles in flight (bulk copies into a shared-memory ring)
+constexpr int L2_NS = 6;          // activation rows in flight with the tensor-map path (3 per row parity)
 constexpr int L2_PD = 3;          // own rows of activation copies in flight per converter warp (= 6 rows ahead)
+
+// 2-D tiled TMA: box {Wm pixels, C planes} of the [planes][pixels] view of an activation tensor <-> dense [C][Wm] shared memory.
+// The tensor map takes element coordinates, so the 8-byte-aligned rows of the 130-wide planes need no special casing.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(map), "r"(c0), "r"(c1), "r"(smem_u32(src))
+               : "memory");
+}
 
 __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
@@ -148,27 +165,31 @@ constexpr int HE_PB = 8;      // planes per block
 template <int M1T>
 __global__ void __launch_bounds__(256)
 hinv_edge_kernel(const float2* __restrict__ Y, float* __restrict__ E, const float* __restrict__ twH,
-                 const float* __restrict__ twW, int H, int W, int WP, int Wm, int RE, int r_edge, int m1, int m2, long planes,
-                 int cmode, float scale) {
+                 const float* __restrict__ twW, int H, int W, int WP, int Wm, int RE, int r_edge, int shift, int m1, int m2,
+                 long planes, int cmode, float scale) {
   constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
   __shared__ float2 U[HE_PB][2 * M1T][L2_RMAX];
   const long p0 = (long)blockIdx.x * HE_PB;
   const int R = 2 * m1;
-  for (int i = threadIdx.x; i < HE_PB * R * RE; i += blockDim.x) {
-    const int j = i % RE, r = (i / RE) % R, pl = i / (RE * R);
+  // column slot u: u < r_edge -> w = Wm + u (rows whose window is [0, Wm)); with `shift`, r_edge <= u < 2 r_edge ->
+  // w = u - r_edge (rows whose tensor-map window is [r_edge, Wm + r_edge))
+  const int ncol = shift ? 2 * r_edge : r_edge;
+  for (int i = threadIdx.x; i < HE_PB * R * L2_RMAX; i += blockDim.x) {
+    const int u = i % L2_RMAX, r = (i / L2_RMAX) % R, pl = i / (L2_RMAX * R);
     float2 acc = make_float2(0.f, 0.f);
-    if (p0 + pl < planes && j < r_edge) {
+    if (p0 + pl < planes && u < ncol) {
+      const int wcol = u < r_edge ? Wm + u : u - r_edge;
       const float2* __restrict__ yp = Y + ((size_t)(p0 + pl) * R + r) * m2;
       for (int q = 0; q < m2; ++q) {
         float sc = scale;
         if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
         const float2 y = __ldg(yp + q);
-        const float c = sc * __ldg(twW + (size_t)q * WP + Wm + j), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + Wm + j);
+        const float c = sc * __ldg(twW + (size_t)q * WP + wcol), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + wcol);
         acc.x = fmaf(y.x, c, acc.x); acc.x = fmaf(-y.y, sn, acc.x);
         acc.y = fmaf(y.x, sn, acc.y); acc.y = fmaf(y.y, c, acc.y);
       }
     }
-    U[pl][r][j] = acc;
+    U[pl][r][u] = acc;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < HE_PB * H; i += blockDim.x) {
@@ -192,8 +213,11 @@ hinv_edge_kernel(const float2* __restrict__ Y, float* __restrict__ E, const floa
         e[j] = fmaf(v.x, c, e[j]); e[j] = fmaf(v.y, sn, e[j]);
       }
     }
+    const int u0 = (shift && (((unsigned)h * (unsigned)W) & 3u)) ? r_edge : 0;
     float* __restrict__ o = E + ((size_t)(p0 + pl) * H + h) * RE;
-    for (int j = 0; j < RE; ++j) o[j] = e[j];
+#pragma unroll
+    for (int j = 0; j < L2_RMAX; ++j)
+      if (j < RE) o[j] = (u0 == 0) ? e[j] : ((j + 2 < L2_RMAX) ? e[(j + 2) & (L2_RMAX - 1)] : 0.f);      // shift only with r_edge = 2
   }
 }
 
@@ -213,7 +237,7 @@ struct L2Cfg {
   static constexpr int BPREP_WARPS = 2;
   static constexpr int NFB = NPAD / 4;                           // float4 of a T2 tile per B-prep lane (KQ <= 32)
   static constexpr int THREADS = 32 * (MMA_WARP + 2 + BPREP_WARPS);
-  static constexpr unsigned TM_COLS = (2 * 32 + 4 * KA + 2 * NPAD <= 256) ? 256u : 512u;
+  static constexpr unsigned TM_COLS = (4 * 32 + 4 * KA + 2 * NPAD <= 256) ? 256u : 512u;
 };
 
 struct L2Args {
@@ -230,6 +254,7 @@ struct L2Args {
   int tile_floats;
   long total_tiles;     // B * RS
   int transpose_w, apply_gelu, single;
+  int shift;            // tensor-map path, W % 4 == 2: rows with (row * W) % 4 == 2 use the column window [2, 130) (16-byte aligned)
   FastDiv rs_div;
   unsigned long long* trace;
   int dbg;   // L2_TRACE builds only: 1 no epilogue stores, 2 no activation loads, 4 no MMAs, 8 no edge, 16 no STTM, 32 no LDTM
@@ -248,9 +273,11 @@ struct IC { static constexpr int value = V; };
 #endif
 
 // CX: compile-time width (0 = run-time p.C, every channel loop predicated); GELU / SOUT: epilogue form
-template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT>
+//     TMA: activation rows come in and results go out through 2-D tensor maps (one TMA op per row for all channels)
+template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT, bool TMA>
 __global__ void __launch_bounds__(L2Cfg<KA, NPAD, CWQ>::THREADS, 1)
-layer2d_tc_kernel(const L2Args p) {
+layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_o,
+                  const __grid_constant__ CUtensorMap tm_s) {
   using Cfg = L2Cfg<KA, NPAD, CWQ>;
   extern __shared__ __align__(128) unsigned char lsm[];
   const int KQ = p.KQ, W = p.W;
@@ -263,16 +290,22 @@ layer2d_tc_kernel(const L2Args p) {
   float* eB = eW + C * CP;                                // [NPAD] bias
   float* eF = eB + NPAD;                                  // [L2_RMAX][KQ] twiddles of the edge columns
   float* ring = eF + L2_RMAX * KQ;                        // [L2_NR][tile_floats] raw T2 tiles (bulk-copy destination)
-  float* stage = ring + (size_t)L2_NR * p.tile_floats;    // [CONV_WARPS][L2_PD][KA][32] activation rows (cp.async)
+  // activation staging (128-byte aligned): [CONV_WARPS][L2_PD][KA][32] per-warp rows, filled by cp.async or, with tensor
+  // maps, by one {32 pixels, C planes} box per warp and row; TMA only: [out | s][2][C][Wm] result boxes
+  float* stage = reinterpret_cast<float*>((reinterpret_cast<size_t>(ring + (size_t)L2_NR * p.tile_floats) + 127) & ~size_t(127));
+  const int box_floats = ((C * (p.W < 128 ? p.W : 128) + 31) & ~31);
+  float* ostage = stage + (size_t)Cfg::CONV_WARPS * L2_PD * KA * 32;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
-      (reinterpret_cast<size_t>(stage + (size_t)Cfg::CONV_WARPS * L2_PD * KA * 32) + 15) & ~size_t(15));
+      (reinterpret_cast<size_t>(ostage + (TMA ? (size_t)4 * box_floats : 0)) + 15) & ~size_t(15));
   unsigned long long* a_ready = bars;                  // [2] converters wrote A buffer s
   unsigned long long* mma_done = bars + 2;             // [2] MMAs of the tile on buffers s complete (A / B free, D full)
   unsigned long long* d_free = bars + 4;               // [2] accumulator s read back
   unsigned long long* b_ready = bars + 6;              // [2] T2 operand tile s is split and staged
   unsigned long long* raw_full = bars + 8;             // [L2_NR] bulk copy of a raw T2 tile landed
   unsigned long long* f_ready = bars + 8 + L2_NR;      // [1] the twiddle columns of A are in tensor memory (once)
-  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 9 + L2_NR);
+  unsigned long long* raw_free = bars + 9 + L2_NR;     // [L2_NR] the B-prep warp has read ring slot
+  unsigned long long* act_full = raw_free + L2_NR;     // [CONV_WARPS][L2_PD] TMA: this warp's 32 columns of a row landed
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(act_full + Cfg::CONV_WARPS * L2_PD);
 
   const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
   const int Wm = W < 128 ? W : 128;          // columns on the tensor cores
@@ -296,6 +329,8 @@ layer2d_tc_kernel(const L2Args p) {
     }
     for (int s = 0; s < L2_NR; ++s) mbar_init(raw_full + s, 1);
     mbar_init(f_ready, 4);
+    for (int s = 0; s < L2_NR; ++s) mbar_init(raw_free + s, 1);
+    for (int s = 0; s < Cfg::CONV_WARPS * L2_PD; ++s) mbar_init(act_full + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == Cfg::MMA_WARP) tmem_alloc(tmem_slot, Cfg::TM_COLS);
@@ -329,7 +364,9 @@ layer2d_tc_kernel(const L2Args p) {
   __syncthreads();
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
-  const unsigned TM_FHI = 0, TM_FLO = (unsigned)KQ, TM_A = 2u * KQ, TM_D = 2u * KQ + 4u * KA;
+  // twiddle sets: [hi | lo] for the column window [0, Wm) and, shifted rows, [2, Wm + 2)
+  const unsigned TM_FHI = 0, TM_FLO = (unsigned)KQ, TM_F1 = 2u * KQ, TM_A = 4u * KQ, TM_D = 4u * KQ + 4u * KA;
+  const int shift = TMA ? p.shift : 0;
 
   if (warp < Cfg::CONV_WARPS) {
     // ---- converters: lane = w.  Warp (quadrant, parity) owns ALL bypass columns of its 32 lanes for the rows of its
@@ -342,17 +379,18 @@ layer2d_tc_kernel(const L2Args p) {
     const unsigned ta = tmem_base + ((unsigned)(quad * 32) << 16);
     if (par == 0) {
       // twiddle columns, once: F[w, q'] = twW[q'][w]
-      for (int g = 0; g < KQ / 8; ++g) {
-        float hi[8], lo[8];
+      for (int set = 0; set <= shift; ++set)
+        for (int g = 0; g < KQ / 8; ++g) {
+          float hi[8], lo[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = 8 * g + e;
-          const float v = (wv && k < m2x2) ? __ldg(p.twW + (size_t)k * p.WP + w) : 0.f;
-          split_tf32(v, hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) {
+            const int k = 8 * g + e;
+            const float v = (wv && k < m2x2) ? __ldg(p.twW + (size_t)k * p.WP + w + 2 * set) : 0.f;
+            split_tf32(v, hi[e], lo[e]);
+          }
+          tmem_st8(ta + (set ? TM_F1 : 0u) + TM_FHI + 8u * g, hi);
+          tmem_st8(ta + (set ? TM_F1 : 0u) + TM_FLO + 8u * g, lo);
         }
-        tmem_st8(ta + TM_FHI + 8u * g, hi);
-        tmem_st8(ta + TM_FLO + 8u * g, lo);
-      }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
@@ -367,7 +405,22 @@ layer2d_tc_kernel(const L2Args p) {
     const int s = par;
     float* __restrict__ stg = stage + (size_t)warp * L2_PD * (KA * 32) + lane;      // [L2_PD][KA][32 lanes]
     const unsigned stg_u32 = smem_u32(stg);
+    float* __restrict__ wstage = stage + (size_t)warp * L2_PD * (KA * 32);          // this warp's [L2_PD][KA][32]
+    const unsigned box_bytes = (unsigned)C * 32u * 4u;
     auto load_tile = [&](int it, int slot) {
+      if (TMA) {                                   // one {32 pixels, C planes} box: this warp's columns of row `it`
+        if (lane == 0 && it < ntl && !L2DBG(2)) {
+          const unsigned T = (unsigned)(t_begin + it);
+          const unsigned b = rsd.div(T);
+          const unsigned row = T - b * RS;
+          unsigned long long* bar = act_full + warp * L2_PD + slot;
+          mbar_arrive_expect_tx(bar, box_bytes);
+          const unsigned px = row * (unsigned)W;
+          tma_load_2d(wstage + (size_t)slot * (KA * 32), &tm_a, (int)(px + (shift ? (px & 3u) : 0u)) + quad * 32,
+                      (int)(b * (unsigned)C), bar);
+        }
+        return;
+      }
       if (it < ntl && wv && !L2DBG(2)) {
         const unsigned T = (unsigned)(t_begin + it);
         const unsigned b = rsd.div(T);
@@ -382,13 +435,23 @@ layer2d_tc_kernel(const L2Args p) {
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    auto convert_tile = [&](int it, int slot) {
+    auto convert_tile = [&](int it, int slot, int use) {
       const unsigned ph = ((unsigned)it >> 1) & 1u;
-      asm volatile("cp.async.wait_group %0;" ::"n"(L2_PD - 1) : "memory");          // this row's copies have landed
       float r[NLD];
-      const float* __restrict__ sp = stg + (size_t)slot * (KA * 32);
+      if (TMA) {
+        if (!L2DBG(2)) L2WAIT_COLD(act_full + warp * L2_PD + slot, (unsigned)use & 1u);
+        if (warp == 0) L2TR(1, it);
+        const float* __restrict__ sp = wstage + (size_t)slot * (KA * 32) + lane;
 #pragma unroll
-      for (int i = 0; i < NLD; ++i) r[i] = (wv && i < C) ? sp[i * 32] : 0.f;
+        for (int i = 0; i < NLD; ++i) r[i] = (wv && i < C) ? sp[i * 32] : 0.f;
+        __syncwarp();                              // every lane has read the slot: load_tile below may refill it
+        if (warp == 0) L2TR(2, it);
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(L2_PD - 1) : "memory");        // this row's copies have landed
+        const float* __restrict__ sp = stg + (size_t)slot * (KA * 32);
+#pragma unroll
+        for (int i = 0; i < NLD; ++i) r[i] = (wv && i < C) ? sp[i * 32] : 0.f;
+      }
       L2WAIT_COLD(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read A buffer s
       if (warp == 0) L2TR(0, it);
       tc_fence_after();
@@ -424,11 +487,27 @@ layer2d_tc_kernel(const L2Args p) {
     };
 #pragma unroll
     for (int d = 0; d < L2_PD; ++d) load_tile(par + 2 * d, d);
-    int slot = 0;
+    // T2 ring copies are issued here too (quadrant 0 of each parity), not by the B-prep warps: their proxy fence is a
+    // MEMBAR that waits for the issuing thread's bulk copies in flight
+    const unsigned tile_bytes = (unsigned)p.tile_floats * 4u;
+    auto issue_t2 = [&](int it) {
+      const int rs = it & (L2_NR - 1);
+      mbar_arrive_expect_tx(raw_full + rs, tile_bytes);
+      bulk_g2s(ring + (size_t)rs * p.tile_floats, p.T2g + (size_t)(t_begin + it) * p.tile_floats, tile_bytes, raw_full + rs);
+    };
+    if (quad == 0 && lane == 0) {
+      if (par < ntl) issue_t2(par);
+      if (par + 2 < ntl) issue_t2(par + 2);
+    }
+    int slot = 0, use = 0;                          // use = how many times this slot has been filled before
     for (int it = par; it < ntl; it += 2) {
-      convert_tile(it, slot);
+      convert_tile(it, slot, use);
       load_tile(it + 2 * L2_PD, slot);
-      slot = (slot + 1 == L2_PD) ? 0 : slot + 1;
+      if (quad == 0 && lane == 0 && it + L2_NR < ntl) {
+        L2WAIT_COLD(raw_free + (it & (L2_NR - 1)), ((unsigned)it / L2_NR) & 1u);    // B-prep has read raw tile `it`
+        issue_t2(it + L2_NR);
+      }
+      if (++slot == L2_PD) { slot = 0; ++use; }
     }
   } else if (warp < Cfg::MMA_WARP) {
     // ---- epilogue: thread = w, a slice of the output channels ------------------------------------------
@@ -461,7 +540,32 @@ layer2d_tc_kernel(const L2Args p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(d_free + s);
         if (ew == 0) L2TR(10, it);
-        if (wv && !L2DBG(1)) {
+        if (TMA) {
+          // results -> dense [C][Wm] boxes in shared memory, one tensor-map store per row and tensor
+          float* __restrict__ po = ostage + (size_t)(it & 1) * box_floats + (size_t)c0 * Wm + w;
+          float* __restrict__ ps = po + 2 * box_floats;
+          if (wv && !L2DBG(1)) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (i < cn) {
+                const float x = v[i];
+                if (SOUT) ps[i * Wm] = x;
+                po[i * Wm] = GELU ? gelu_fast(x) : x;
+              }
+            }
+          }
+          fence_proxy_async();                       // staging stores -> visible to the TMA engine
+          const bool issuer = (ew == 0 && lane == 0);
+          if (issuer) bulk_wait_read<0>();           // the store of row it - 1 has read its boxes: row it + 1 may overwrite them
+          named_bar_sync(1, Cfg::EPI_WARPS * 32);
+          if (issuer && !L2DBG(1)) {
+            const unsigned px = row * (unsigned)W;
+            const int c0x = (int)(px + (shift ? (px & 3u) : 0u));
+            tma_store_2d(&tm_o, c0x, (int)(b * (unsigned)C), ostage + (size_t)(it & 1) * box_floats);
+            if (SOUT) tma_store_2d(&tm_s, c0x, (int)(b * (unsigned)C), ostage + (size_t)(2 + (it & 1)) * box_floats);
+            bulk_commit();
+          }
+        } else if (wv && !L2DBG(1)) {
           float* __restrict__ po = obase + toff;
           float* __restrict__ ps = SOUT ? sbase + toff : nullptr;
 #pragma unroll
@@ -476,6 +580,7 @@ layer2d_tc_kernel(const L2Args p) {
         }
         if (ew == 0) L2TR(11, it);
       }
+      if (TMA && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     };
     if (e == 0) role(IC<0>{});
     else if (e == 1) role(IC<1>{});
@@ -495,6 +600,12 @@ layer2d_tc_kernel(const L2Args p) {
       const unsigned td = tmem_base + TM_D + (unsigned)(s * NPAD);
       const unsigned long long d_th = d_t0 + (unsigned long long)(2 * s) * t2d, d_tl = d_th + t2d;
       const unsigned ab = tmem_base + TM_A + (unsigned)(s * 2 * KA);
+      unsigned fbase = tmem_base;
+      if (shift) {
+        const unsigned T = (unsigned)(t_begin + it);
+        const unsigned row = T - rsd.div(T) * RS;
+        if ((row * (unsigned)W) & 3u) fbase += TM_F1;
+      }
       L2WAIT_HOT(d_free + s, ph ^ 1u);
       L2WAIT_HOT(b_ready + s, ph);
       L2TR(6, it);
@@ -504,7 +615,7 @@ layer2d_tc_kernel(const L2Args p) {
       for (int ks = 0; ks < 4; ++ks) {
         if (ks < nkq && !L2DBG(4)) {
           const unsigned long long fo = (unsigned long long)(ks * 16);
-          const unsigned fh = tmem_base + TM_FHI + 8u * ks, fl = tmem_base + TM_FLO + 8u * ks;
+          const unsigned fh = fbase + TM_FHI + 8u * ks, fl = fbase + TM_FLO + 8u * ks;
           if (!single) {
             tc_mma_tf32_ts_elect(td, fl, d_th + fo, idesc, ks != 0);
             tc_mma_tf32_ts_elect(td, fh, d_tl + fo, idesc, 1u);
@@ -530,27 +641,16 @@ layer2d_tc_kernel(const L2Args p) {
       L2TR(8, it);
     }
   } else if (warp >= Cfg::BPREP_WARP0) {
-    // ---- T2 operand tiles: warp j owns the rows of parity j, i.e. operand buffer s = j and ring slots j, j + 2.
-    // lane 0 bulk-copies the raw tile (2.3 KB at cfg 1) into the ring two own rows ahead; the warp splits it hi / lo
-    // into the operand buffer.  These warps have no global traffic of their own in flight, so the proxy fence their
-    // shared-memory stores need (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) is cheap here.
+    // ---- T2 operand tiles: warp j owns the rows of parity j, i.e. operand buffer s = j and ring slots j, j + 2: it
+    // splits the raw tile (2.3 KB at cfg 1, bulk-copied into the ring by a converter warp) hi / lo into the operand
+    // buffer.  These warps have no memory traffic of their own in flight -- no loads, stores or bulk copies --, so the
+    // proxy fence their shared-memory stores need (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) is cheap here.
     constexpr int NFB = Cfg::NFB;
     const int j = warp - Cfg::BPREP_WARP0, s = j;
     const int tile_f4 = p.tile_floats >> 2;
     const float4* __restrict__ ring4 = reinterpret_cast<const float4*>(ring) + lane;
     float4* __restrict__ dh = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s) * t2_tile) + lane;
     float4* __restrict__ dl = reinterpret_cast<float4*>(bT2 + (size_t)(2 * s + 1) * t2_tile) + lane;
-    const unsigned tile_bytes = (unsigned)p.tile_floats * 4u;
-    auto issue = [&](int it) {                          // one bulk copy per raw T2 tile into the ring
-      const int slot = it & (L2_NR - 1);
-      mbar_arrive_expect_tx(raw_full + slot, tile_bytes);
-      bulk_g2s(ring + (size_t)slot * p.tile_floats, p.T2g + (size_t)(t_begin + it) * p.tile_floats, tile_bytes, raw_full + slot);
-    };
-    if (lane == 0) {
-      if (j < ntl) issue(j);
-      if (j + 2 < ntl) issue(j + 2);
-    }
-    __syncwarp();
     for (int it = j; it < ntl; it += 2) {
       const unsigned ph = ((unsigned)it >> 1) & 1u;
       const int slot = it & (L2_NR - 1);
@@ -561,7 +661,7 @@ layer2d_tc_kernel(const L2Args p) {
       for (int i = 0; i < NFB; ++i)
         if (lane + 32 * i < tile_f4) raw[i] = ring4[(size_t)slot * tile_f4 + 32 * i];
       __syncwarp();
-      if (lane == 0 && it + L2_NR < ntl) issue(it + L2_NR);          // the slot has been read: refill it
+      if (lane == 0) mbar_arrive(raw_free + slot);                   // the slot has been read: the converter may refill it
       L2WAIT_COLD(mma_done + s, ph ^ 1u);          // the MMAs of tile it - 2 no longer read B buffer s
       if (j == 0) L2TR(13, it);
 #pragma unroll
@@ -583,9 +683,9 @@ layer2d_tc_kernel(const L2Args p) {
     // ---- edge warp: the W - 128 columns that do not fit the TMEM lanes, on the FP32 pipes, independent of the
     // pipeline.  lane = row, 32 rows per pass: spectral part from hinv_edge_kernel (coalesced over the rows), bypass
     // = C x C FMAs per column with the weights as shared-memory broadcasts; all loads of a pass are issued up front.
-    const float* __restrict__ abase = p.a + Wm;
-    float* __restrict__ obase = p.out + Wm;
-    float* __restrict__ sbase = SOUT ? p.s_out + Wm : nullptr;
+    const float* __restrict__ abase = p.a;
+    float* __restrict__ obase = p.out;
+    float* __restrict__ sbase = SOUT ? p.s_out : nullptr;
     const int RE = p.RE;
     const bool pair_ok = ((W & 1) == 0) && ((reinterpret_cast<size_t>(p.a) & 7) == 0);
     for (int base = 0; base < ntl; base += 32) {
@@ -593,7 +693,8 @@ layer2d_tc_kernel(const L2Args p) {
       const unsigned T = (unsigned)(t_begin + (live ? base + lane : ntl - 1));
       const unsigned b = rsd.div(T);
       const unsigned row = T - b * RS;
-      const size_t roff = (size_t)b * bs + (size_t)row * W;
+      // this row's edge columns: [Wm, W), or [0, W - Wm) where the tensor-map window is shifted
+      const size_t roff = (size_t)b * bs + (size_t)row * W + ((shift && ((row * (unsigned)W) & 3u)) ? 0 : Wm);
       const float* __restrict__ erow = p.E + ((size_t)b * C * RS + row) * RE;       // + co * RS * RE
       for (int j0 = 0; j0 < r_edge; j0 += 2) {             // two edge columns per pass
         const bool two = j0 + 1 < r_edge;
@@ -653,43 +754,107 @@ layer2d_tc_kernel(const L2Args p) {
 }
 
 template <int KA, int NPAD, int CWQ>
-size_t layer2d_smem_bytes(int KQ, int C) {
+size_t layer2d_smem_bytes(int KQ, int C, int Wm, bool tma) {
   const size_t CP = (size_t)((C + 3) & ~3);
+  const size_t box = (size_t)((C * Wm + 31) & ~31);
+  const size_t staging = (size_t)8 * L2_PD * KA * 32 + (tma ? 4 * box : 0);
   return sizeof(float) * ((size_t)4 * NPAD * KQ + 2 * NPAD * KA + (size_t)C * CP + NPAD + L2_RMAX * KQ +
-                          (size_t)L2_NR * ((C + 7) / 8) * KQ * 8 + (size_t)8 * L2_PD * KA * 32) + 16 + (9 + L2_NR) * 8 + 16;
+                          (size_t)L2_NR * ((C + 7) / 8) * KQ * 8 + staging) + 128 + 16 + (9 + 2 * L2_NR + 8 * L2_PD) * 8 + 16;
 }
 
-template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT>
+// ---- tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda) ----------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// [planes][pixels] f32 view of an activation tensor, box {Wm pixels, C planes}
+bool make_act_map(CUtensorMap* m, const float* base, unsigned long long pixels, unsigned long long planes, unsigned Wm, unsigned C) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr || base == nullptr) return false;
+  const cuuint64_t gdim[2] = {pixels, planes};
+  const cuuint64_t gstr[1] = {pixels * 4ull};
+  const cuuint32_t box[2] = {Wm, C};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int KA, int NPAD, int CWQ, int CX, bool GELU, bool SOUT, bool TMA>
 int launch_layer2d_k(const L2Args& args, cudaStream_t st, bool attr_only) {
   using Cfg = L2Cfg<KA, NPAD, CWQ>;
-  const size_t smem = layer2d_smem_bytes<KA, NPAD, CWQ>(args.KQ, args.C);
-  if (smem > 200 * 1024) { set_error("layer2d_tc: shared memory %zu", smem); return FNO_E_ARG; }
+  auto kern = layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT, TMA>;
   if (attr_only) {
-    if (cudaFuncSetAttribute(layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             200 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(layer2d_tc)");
     return FNO_OK;
   }
+  const int Wm = args.W < 128 ? args.W : 128;
+  const size_t smem = layer2d_smem_bytes<KA, NPAD, CWQ>(args.KQ, args.C, Wm, TMA);
+  if (smem > 200 * 1024) { set_error("layer2d_tc: shared memory %zu", smem); return FNO_E_ARG; }
+  CUtensorMap ma, mo, ms;
+  memset(&ma, 0, sizeof(ma)); memset(&mo, 0, sizeof(mo)); memset(&ms, 0, sizeof(ms));
+  if (TMA) {
+    const unsigned long long pixels = (unsigned long long)args.RS * args.W, planes = (unsigned long long)(args.total_tiles / args.RS) * args.C;
+    if (!make_act_map(&ma, args.a, pixels, planes, 32, args.C) || !make_act_map(&mo, args.out, pixels, planes, Wm, args.C) ||
+        (SOUT && !make_act_map(&ms, args.s_out, pixels, planes, Wm, args.C))) {
+      set_error("layer2d_tc: cuTensorMapEncodeTiled failed");
+      return FNO_E_CUDA;
+    }
+  }
   const long ctas = args.total_tiles < 148 ? args.total_tiles : 148;
-  layer2d_tc_kernel<KA, NPAD, CWQ, CX, GELU, SOUT><<<(unsigned)ctas, Cfg::THREADS, smem, st>>>(args);
+  kern<<<(unsigned)ctas, Cfg::THREADS, smem, st>>>(args, ma, mo, ms);
   count_launch();
   return check_launch("layer2d_tc_kernel");
 }
 
-template <int KA, int NPAD, int CWQ, int CX>
-int launch_layer2d_t(const L2Args& args, cudaStream_t st, bool attr_only = false) {
+// tensor-map eligibility: 16-byte aligned tensors and plane pitch, box rows a multiple of 16 bytes
+bool layer2d_tma_ok(const L2Args& a) {
+  static const bool off = [] { const char* e = std::getenv("FNO_LAYER_TMA"); return e != nullptr && e[0] == '0'; }();
+  if (off || encode_tiled_fn() == nullptr) return false;
+  const int Wm = a.W < 128 ? a.W : 128;
+  if (((long)a.RS * a.W) % 4 != 0 || Wm % 4 != 0 || (long)a.RS * a.W >= (1L << 31)) return false;
+  // every row's column window must start 16-byte aligned: W % 4 == 0, or W = 130 (window [2, 130) on odd rows)
+  if (a.W % 4 != 0 && !(a.W % 4 == 2 && a.W == Wm + 2)) return false;
+  if (((reinterpret_cast<size_t>(a.a) | reinterpret_cast<size_t>(a.out) | reinterpret_cast<size_t>(a.s_out)) & 15) != 0) return false;
+  return true;
+}
+
+template <int KA, int NPAD, int CWQ, int CX, bool TMA>
+int launch_layer2d_m(const L2Args& args, cudaStream_t st, bool attr_only) {
   if (attr_only) {                         // once per device: raise the dynamic shared-memory limit of all four forms
-    int rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st, true);
-    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st, true);
-    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st, true);
-    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st, true);
+    int rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, true, TMA>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, true, false, TMA>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, true, TMA>(args, st, true);
+    if (rc == FNO_OK) rc = launch_layer2d_k<KA, NPAD, CWQ, CX, false, false, TMA>(args, st, true);
     return rc;
   }
   const bool so = args.s_out != nullptr;
-  if (args.apply_gelu) return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, true, true>(args, st, false)
-                                 : launch_layer2d_k<KA, NPAD, CWQ, CX, true, false>(args, st, false);
-  return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, false, true>(args, st, false)
-            : launch_layer2d_k<KA, NPAD, CWQ, CX, false, false>(args, st, false);
+  if (args.apply_gelu) return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, true, true, TMA>(args, st, false)
+                                 : launch_layer2d_k<KA, NPAD, CWQ, CX, true, false, TMA>(args, st, false);
+  return so ? launch_layer2d_k<KA, NPAD, CWQ, CX, false, true, TMA>(args, st, false)
+            : launch_layer2d_k<KA, NPAD, CWQ, CX, false, false, TMA>(args, st, false);
+}
+
+template <int KA, int NPAD, int CWQ, int CX>
+int launch_layer2d_t(const L2Args& args, cudaStream_t st, bool attr_only = false) {
+  if (attr_only) {
+    const int rc = launch_layer2d_m<KA, NPAD, CWQ, CX, true>(args, st, true);
+    return rc != FNO_OK ? rc : launch_layer2d_m<KA, NPAD, CWQ, CX, false>(args, st, true);
+  }
+  return layer2d_tma_ok(args) ? launch_layer2d_m<KA, NPAD, CWQ, CX, true>(args, st, false)
+                              : launch_layer2d_m<KA, NPAD, CWQ, CX, false>(args, st, false);
 }
 
 template <int M1T>
@@ -747,11 +912,11 @@ size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C) {
 }
 
 template <int M1T>
-int launch_hinv_edge_t(const Plan* p, const float* Y, float* E, long planes, int cmode, float scale, cudaStream_t st) {
+int launch_hinv_edge_t(const Plan* p, const float* Y, float* E, long planes, int shift, int cmode, float scale, cudaStream_t st) {
   const int Wm = p->W < 128 ? p->W : 128;
   const unsigned grid = (unsigned)((planes + HE_PB - 1) / HE_PB);
   hinv_edge_kernel<M1T><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(Y), E, p->twH, p->twW, p->H, p->W, p->WP, Wm,
-                                              re_of(p), p->W - Wm, p->m1, p->m2, planes, cmode, scale);
+                                              re_of(p), p->W - Wm, shift, p->m1, p->m2, planes, cmode, scale);
   count_launch();
   return check_launch("hinv_edge_kernel");
 }
@@ -777,20 +942,22 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
   }
   if (rc != FNO_OK) return rc;
   float* E = work + (size_t)total * tile_floats;             // 8-byte aligned: tile_floats is a multiple of 64
+  L2Args args;
+  args.a = a; args.out = out; args.s_out = s_out; args.W = p->W; args.RS = p->D1 * p->H;
+  const int shift = (layer2d_tma_ok(args) && p->W % 4 == 2) ? 1 : 0;
   if (p->W > 128) {
     const long planes = (long)B * C * p->D1;
     switch (p->M1T) {
-      case 4: rc = launch_hinv_edge_t<4>(p, Y, E, planes, cmode, scale, st); break;
-      case 8: rc = launch_hinv_edge_t<8>(p, Y, E, planes, cmode, scale, st); break;
-      case 12: rc = launch_hinv_edge_t<12>(p, Y, E, planes, cmode, scale, st); break;
-      case 16: rc = launch_hinv_edge_t<16>(p, Y, E, planes, cmode, scale, st); break;
-      case 24: rc = launch_hinv_edge_t<24>(p, Y, E, planes, cmode, scale, st); break;
-      default: rc = launch_hinv_edge_t<32>(p, Y, E, planes, cmode, scale, st); break;
+      case 4: rc = launch_hinv_edge_t<4>(p, Y, E, planes, shift, cmode, scale, st); break;
+      case 8: rc = launch_hinv_edge_t<8>(p, Y, E, planes, shift, cmode, scale, st); break;
+      case 12: rc = launch_hinv_edge_t<12>(p, Y, E, planes, shift, cmode, scale, st); break;
+      case 16: rc = launch_hinv_edge_t<16>(p, Y, E, planes, shift, cmode, scale, st); break;
+      case 24: rc = launch_hinv_edge_t<24>(p, Y, E, planes, shift, cmode, scale, st); break;
+      default: rc = launch_hinv_edge_t<32>(p, Y, E, planes, shift, cmode, scale, st); break;
     }
     if (rc != FNO_OK) return rc;
   }
-  L2Args args;
-  args.E = E; args.RE = re_of(p);
+  args.E = E; args.RE = re_of(p); args.shift = shift;
   args.a = a; args.T2g = work; args.Wl = Wl; args.bias = bias; args.s_out = s_out; args.out = out;
   args.twW = p->twW; args.WP = p->WP; args.W = p->W; args.m2 = p->m2; args.KQ = KQ; args.C = C;
   args.RS = p->D1 * p->H; args.tile_floats = tile_floats; args.total_tiles = total;
