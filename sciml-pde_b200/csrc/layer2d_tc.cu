@@ -77,6 +77,93 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
 }
 
 // ------------------------------------------------------------------------------------------------------
+// spectral part of the edge columns w = Wm + j (j < RE) that do not fit the 128 TMEM lanes:
+//   E[plane, h, j] = Re sum_{r, q} sc_q Y[r, q] e^{+2 pi i (k_r h / H + q w_j / W)}
+// contiguous axis first (U[r, j] = sum_q sc_q Y[r, q] e^{i phi_q w_j}, 2 m1 x RE complex numbers per plane, shared
+// memory), then the strided axis per row.  0.1 % of the layer's flops; the main kernel's edge warp adds the bypass.
+// ------------------------------------------------------------------------------------------------------
+constexpr int HE_PB = 4;      // planes per block
+struct EdgeArgs {
+  float* E;             // [planes][H][RE]
+  const float* twW;
+  int WP, Wm, RE, r_edge, shift;
+};
+
+template <int M1T>
+__device__ __forceinline__ void hinv_edge_block(const float2* __restrict__ Y, const EdgeArgs& ea, const float* __restrict__ twH,
+                                                int H, int W, int m1, int m2, long p0, long planes, int cmode, float scale) {
+  constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
+  __shared__ float2 U[HE_PB][2 * M1T][L2_RMAX];
+  __shared__ float2 PM[HE_PB][M1T + 1][L2_RMAX];      // (Re(U[+j] + U[-j]), Im(U[+j] - U[-j])): all the real part needs
+  float* __restrict__ E = ea.E;
+  const float* __restrict__ twW = ea.twW;
+  const int WP = ea.WP, Wm = ea.Wm, RE = ea.RE, r_edge = ea.r_edge, shift = ea.shift;
+  const int R = 2 * m1;
+  // column slot u: u < r_edge -> w = Wm + u (rows whose window is [0, Wm)); with `shift`, r_edge <= u < 2 r_edge ->
+  // w = u - r_edge (rows whose tensor-map window is [r_edge, Wm + r_edge))
+  const int ncol = shift ? 2 * r_edge : r_edge;
+  for (int i = threadIdx.x; i < HE_PB * R * L2_RMAX; i += blockDim.x) {
+    const int u = i % L2_RMAX, r = (i / L2_RMAX) % R, pl = i / (L2_RMAX * R);
+    float2 acc = make_float2(0.f, 0.f);
+    if (p0 + pl < planes && u < ncol) {
+      const int wcol = u < r_edge ? Wm + u : u - r_edge;
+      const float2* __restrict__ yp = Y + ((size_t)(p0 + pl) * R + r) * m2;
+#pragma unroll 4
+      for (int q = 0; q < m2; ++q) {
+        float sc = scale;
+        if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
+        const float2 y = __ldg(yp + q);
+        const float c = sc * __ldg(twW + (size_t)q * WP + wcol), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + wcol);
+        acc.x = fmaf(y.x, c, acc.x); acc.x = fmaf(-y.y, sn, acc.x);
+        acc.y = fmaf(y.x, sn, acc.y); acc.y = fmaf(y.y, c, acc.y);
+      }
+    }
+    U[pl][r][u] = acc;
+  }
+  __syncthreads();
+  // fold the signed frequencies: Re sum_k U[k] e^{i k x} = U[0].x + sum_j (Re(U[j] + U[-j]) cos(j x) - Im(U[j] - U[-j]) sin(j x))
+  for (int i = threadIdx.x; i < HE_PB * (m1 + 1) * L2_RMAX; i += blockDim.x) {
+    const int u = i % L2_RMAX, jj = (i / L2_RMAX) % (m1 + 1), pl = i / (L2_RMAX * (m1 + 1));
+    float2 v;
+    if (jj == 0) {
+      v = make_float2(U[pl][0][u].x, 0.f);
+    } else {
+      const float2 up = (jj < m1) ? U[pl][jj][u] : make_float2(0.f, 0.f);
+      const float2 un = U[pl][R - jj][u];
+      v = make_float2(up.x + un.x, up.y - un.y);
+    }
+    PM[pl][jj][u] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HE_PB * H; i += blockDim.x) {
+    const int h = i % H, pl = i / H;
+    if (p0 + pl >= planes) break;
+    const int t = (2 * h <= H) ? h : H - h;
+    const float sg = (2 * h <= H) ? 1.0f : -1.0f;
+    const float* __restrict__ tw = twH + (size_t)t * JP;
+    const int u0 = (shift && (((unsigned)h * (unsigned)W) & 3u)) ? r_edge : 0;       // this row's column slots
+    float e0 = PM[pl][0][u0].x, e1 = (u0 + 1 < L2_RMAX) ? PM[pl][0][u0 + 1].x : 0.f;
+    float e2 = 0.f, e3 = 0.f;
+    if (RE > 2) { e2 = PM[pl][0][2].x; e3 = PM[pl][0][3].x; }
+    for (int jj = 1; jj <= m1; ++jj) {
+      const float c = __ldg(tw + jj), sn = sg * __ldg(tw + M1T + jj);
+      const float2 a0 = PM[pl][jj][u0], a1 = PM[pl][jj][(u0 + 1) & (L2_RMAX - 1)];
+      e0 = fmaf(a0.x, c, e0); e0 = fmaf(-a0.y, sn, e0);
+      e1 = fmaf(a1.x, c, e1); e1 = fmaf(-a1.y, sn, e1);
+      if (RE > 2) {
+        const float2 a2 = PM[pl][jj][2], a3 = PM[pl][jj][3];
+        e2 = fmaf(a2.x, c, e2); e2 = fmaf(-a2.y, sn, e2);
+        e3 = fmaf(a3.x, c, e3); e3 = fmaf(-a3.y, sn, e3);
+      }
+    }
+    float* __restrict__ o = E + ((size_t)(p0 + pl) * H + h) * RE;
+    o[0] = e0;
+    o[1] = e1;
+    if (RE > 2) { o[2] = e2; o[3] = e3; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // strided-axis inverse into B-operand tiles:  Z[h, q] = sum_r Y[r, q] e^{+2 pi i k_r h / H}  (k_r signed),
 //   T2[(b, h)][n = c][k = q]      =  sc_q Re Z,      T2[..][c][m2 + q] = -sc_q Im Z
 // (sc_q = scale * c2r weight).  Frequencies are folded onto j = |k| and rows onto pairs (t, H - t):
@@ -87,8 +174,26 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
 template <int M1T>
 __global__ void __launch_bounds__(256)
 hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const float* __restrict__ twH, int H, int W,
-                  int m1, int m2, int C, int D1, int KQ, int tile_floats, int TL, int cmode, float scale) {
+                  int m1, int m2, int C, int D1, int KQ, int tile_floats, int TL, int cmode, float scale, const EdgeArgs ea) {
   constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
+  if (blockIdx.z == (C + 7) / 8) {
+    // extra blocks of the same launch: the spectral part of the edge columns for a slice of this sample's channels
+    const int cpb = (C + (int)gridDim.y - 1) / (int)gridDim.y;          // channels per block
+    const int c_lo = blockIdx.y * cpb, c_hi = (c_lo + cpb < C) ? c_lo + cpb : C;
+    const long bd = blockIdx.x;                                        // b * D1 + d1
+    const long b = bd / D1, d1 = bd - b * D1;
+    for (int c0 = c_lo; c0 < c_hi; c0 += HE_PB) {
+      // planes (b * C + c) * D1 + d1 are D1 apart: handle one at a time when D1 > 1
+      if (D1 == 1) {
+        hinv_edge_block<M1T>(Y, ea, twH, H, W, m1, m2, b * C + c0, b * C + c_hi, cmode, scale);
+      } else {
+        for (int c = c0; c < c_hi && c < c0 + HE_PB; ++c)
+          hinv_edge_block<M1T>(Y, ea, twH, H, W, m1, m2, (b * C + c) * D1 + d1, (b * C + c) * D1 + d1 + 1, cmode, scale);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   const int q = threadIdx.x % m2, cl = threadIdx.x / m2;
   const int c = blockIdx.z * 8 + cl;
   if (cl >= 8) return;
@@ -152,72 +257,6 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
       o2[o_im] = -sc * (ei - odi);
       for (int k = 2 * m2 + q; k < KQ; k += m2) o2[eoff + (k >> 2) * 32 + (k & 3)] = 0.f;
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// spectral part of the edge columns w = Wm + j (j < RE) that do not fit the 128 TMEM lanes:
-//   E[plane, h, j] = Re sum_{r, q} sc_q Y[r, q] e^{+2 pi i (k_r h / H + q w_j / W)}
-// contiguous axis first (U[r, j] = sum_q sc_q Y[r, q] e^{i phi_q w_j}, 2 m1 x RE complex numbers per plane, shared
-// memory), then the strided axis per row.  0.1 % of the layer's flops; the main kernel's edge warp adds the bypass.
-// ------------------------------------------------------------------------------------------------------
-constexpr int HE_PB = 8;      // planes per block
-template <int M1T>
-__global__ void __launch_bounds__(256)
-hinv_edge_kernel(const float2* __restrict__ Y, float* __restrict__ E, const float* __restrict__ twH,
-                 const float* __restrict__ twW, int H, int W, int WP, int Wm, int RE, int r_edge, int shift, int m1, int m2,
-                 long planes, int cmode, float scale) {
-  constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
-  __shared__ float2 U[HE_PB][2 * M1T][L2_RMAX];
-  const long p0 = (long)blockIdx.x * HE_PB;
-  const int R = 2 * m1;
-  // column slot u: u < r_edge -> w = Wm + u (rows whose window is [0, Wm)); with `shift`, r_edge <= u < 2 r_edge ->
-  // w = u - r_edge (rows whose tensor-map window is [r_edge, Wm + r_edge))
-  const int ncol = shift ? 2 * r_edge : r_edge;
-  for (int i = threadIdx.x; i < HE_PB * R * L2_RMAX; i += blockDim.x) {
-    const int u = i % L2_RMAX, r = (i / L2_RMAX) % R, pl = i / (L2_RMAX * R);
-    float2 acc = make_float2(0.f, 0.f);
-    if (p0 + pl < planes && u < ncol) {
-      const int wcol = u < r_edge ? Wm + u : u - r_edge;
-      const float2* __restrict__ yp = Y + ((size_t)(p0 + pl) * R + r) * m2;
-      for (int q = 0; q < m2; ++q) {
-        float sc = scale;
-        if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
-        const float2 y = __ldg(yp + q);
-        const float c = sc * __ldg(twW + (size_t)q * WP + wcol), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + wcol);
-        acc.x = fmaf(y.x, c, acc.x); acc.x = fmaf(-y.y, sn, acc.x);
-        acc.y = fmaf(y.x, sn, acc.y); acc.y = fmaf(y.y, c, acc.y);
-      }
-    }
-    U[pl][r][u] = acc;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < HE_PB * H; i += blockDim.x) {
-    const int h = i % H, pl = i / H;
-    if (p0 + pl >= planes) break;
-    const int t = (2 * h <= H) ? h : H - h;
-    const float sg = (2 * h <= H) ? 1.0f : -1.0f;
-    const float* __restrict__ tw = twH + (size_t)t * JP;
-    float e[L2_RMAX];
-#pragma unroll
-    for (int j = 0; j < L2_RMAX; ++j) e[j] = U[pl][0][j].x;          // k = 0
-    for (int jj = 1; jj <= m1; ++jj) {
-      const float c = __ldg(tw + jj), sn = sg * __ldg(tw + M1T + jj);
-#pragma unroll
-      for (int j = 0; j < L2_RMAX; ++j) {
-        if (jj < m1) {                                                // k = +jj (row jj)
-          const float2 u = U[pl][jj][j];
-          e[j] = fmaf(u.x, c, e[j]); e[j] = fmaf(-u.y, sn, e[j]);
-        }
-        const float2 v = U[pl][R - jj][j];                            // k = -jj (row 2 m1 - jj)
-        e[j] = fmaf(v.x, c, e[j]); e[j] = fmaf(v.y, sn, e[j]);
-      }
-    }
-    const int u0 = (shift && (((unsigned)h * (unsigned)W) & 3u)) ? r_edge : 0;
-    float* __restrict__ o = E + ((size_t)(p0 + pl) * H + h) * RE;
-#pragma unroll
-    for (int j = 0; j < L2_RMAX; ++j)
-      if (j < RE) o[j] = (u0 == 0) ? e[j] : ((j + 2 < L2_RMAX) ? e[(j + 2) & (L2_RMAX - 1)] : 0.f);      // shift only with r_edge = 2
   }
 }
 
@@ -859,7 +898,7 @@ int launch_layer2d_t(const L2Args& args, cudaStream_t st, bool attr_only = false
 
 template <int M1T>
 int launch_hinv_t(const Plan* p, const float* Y, float* T2g, int B, int C, int KQ, int tile_floats, int cmode, float scale,
-                  cudaStream_t st) {
+                  const EdgeArgs& ea, cudaStream_t st) {
   const int NP = p->H / 2 + 1;
   int threads = 8 * p->m2;
   threads = (threads + 31) & ~31;
@@ -870,9 +909,10 @@ int launch_hinv_t(const Plan* p, const float* Y, float* T2g, int B, int C, int K
   if (TS > NP) TS = NP;
   const int TL = (NP + TS - 1) / TS;
   TS = (NP + TL - 1) / TL;
-  dim3 grid((unsigned)(B * p->D1), (unsigned)TS, (unsigned)((C + 7) / 8));
+  // one more z-slice of blocks computes the spectral part of the edge columns (W > 128) in the same launch
+  dim3 grid((unsigned)(B * p->D1), (unsigned)TS, (unsigned)((C + 7) / 8 + (ea.r_edge > 0 ? 1 : 0)));
   hinv_tiles_kernel<M1T><<<grid, threads, 0, st>>>(reinterpret_cast<const float2*>(Y), T2g, p->twH, p->H, p->W, p->m1, p->m2,
-                                                  C, p->D1, KQ, tile_floats, TL, cmode, scale);
+                                                  C, p->D1, KQ, tile_floats, TL, cmode, scale, ea);
   count_launch();
   return check_launch("hinv_tiles_kernel");
 }
@@ -911,16 +951,6 @@ size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C) {
   return sizeof(float) * ((size_t)B * p->D1 * p->H * tile_floats_of(p, C) + (size_t)B * C * p->D1 * p->H * re_of(p));
 }
 
-template <int M1T>
-int launch_hinv_edge_t(const Plan* p, const float* Y, float* E, long planes, int shift, int cmode, float scale, cudaStream_t st) {
-  const int Wm = p->W < 128 ? p->W : 128;
-  const unsigned grid = (unsigned)((planes + HE_PB - 1) / HE_PB);
-  hinv_edge_kernel<M1T><<<grid, 256, 0, st>>>(reinterpret_cast<const float2*>(Y), E, p->twH, p->twW, p->H, p->W, p->WP, Wm,
-                                              re_of(p), p->W - Wm, shift, p->m1, p->m2, planes, cmode, scale);
-  count_launch();
-  return check_launch("hinv_edge_kernel");
-}
-
 // out = act( K3(Y) + Wl a + bias ),  s_out = pre-activation (optional);  transpose_w: Wl^T a (adjoint)
 int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float* Wl, const float* bias, float* s_out,
                       float* out, float* work, int B, int C, int cmode, float scale, int apply_gelu, int transpose_w,
@@ -930,33 +960,24 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
   const int KQ = kq_of(p), tile_floats = tile_floats_of(p, C);
   const long total = (long)B * p->D1 * p->H;
   if (total >= (1L << 32)) { set_error("layer2d_tc: too many rows"); return FNO_E_ARG; }
-  int rc;
-  switch (p->M1T) {
-    case 4: rc = launch_hinv_t<4>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    case 8: rc = launch_hinv_t<8>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    case 12: rc = launch_hinv_t<12>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    case 16: rc = launch_hinv_t<16>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    case 24: rc = launch_hinv_t<24>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    case 32: rc = launch_hinv_t<32>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, st); break;
-    default: set_error("unsupported padded modes1 %d", p->M1T); return FNO_E_ARG;
-  }
-  if (rc != FNO_OK) return rc;
   float* E = work + (size_t)total * tile_floats;             // 8-byte aligned: tile_floats is a multiple of 64
   L2Args args;
   args.a = a; args.out = out; args.s_out = s_out; args.W = p->W; args.RS = p->D1 * p->H;
   const int shift = (layer2d_tma_ok(args) && p->W % 4 == 2) ? 1 : 0;
-  if (p->W > 128) {
-    const long planes = (long)B * C * p->D1;
-    switch (p->M1T) {
-      case 4: rc = launch_hinv_edge_t<4>(p, Y, E, planes, shift, cmode, scale, st); break;
-      case 8: rc = launch_hinv_edge_t<8>(p, Y, E, planes, shift, cmode, scale, st); break;
-      case 12: rc = launch_hinv_edge_t<12>(p, Y, E, planes, shift, cmode, scale, st); break;
-      case 16: rc = launch_hinv_edge_t<16>(p, Y, E, planes, shift, cmode, scale, st); break;
-      case 24: rc = launch_hinv_edge_t<24>(p, Y, E, planes, shift, cmode, scale, st); break;
-      default: rc = launch_hinv_edge_t<32>(p, Y, E, planes, shift, cmode, scale, st); break;
-    }
-    if (rc != FNO_OK) return rc;
+  EdgeArgs ea;
+  ea.E = E; ea.twW = p->twW; ea.WP = p->WP; ea.Wm = p->W < 128 ? p->W : 128; ea.RE = re_of(p); ea.r_edge = p->W - ea.Wm;
+  ea.shift = shift;
+  int rc;
+  switch (p->M1T) {
+    case 4: rc = launch_hinv_t<4>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    case 8: rc = launch_hinv_t<8>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    case 12: rc = launch_hinv_t<12>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    case 16: rc = launch_hinv_t<16>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    case 24: rc = launch_hinv_t<24>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    case 32: rc = launch_hinv_t<32>(p, Y, work, B, C, KQ, tile_floats, cmode, scale, ea, st); break;
+    default: set_error("unsupported padded modes1 %d", p->M1T); return FNO_E_ARG;
   }
+  if (rc != FNO_OK) return rc;
   args.E = E; args.RE = re_of(p); args.shift = shift;
   args.a = a; args.T2g = work; args.Wl = Wl; args.bias = bias; args.s_out = s_out; args.out = out;
   args.twW = p->twW; args.WP = p->WP; args.W = p->W; args.m2 = p->m2; args.KQ = KQ; args.C = C;

@@ -25,9 +25,12 @@ ap.add_argument("--res", type=int, default=128)
 ap.add_argument("--modes", type=int, default=12)
 ap.add_argument("--pad", type=int, default=2)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--tf32", action="store_true")
 args = ap.parse_args()
 
 dev = torch.device("cuda", 0)
+if args.tf32:
+    lib.set_math_mode("tf32")
 torch.manual_seed(0)
 B, C, m, n = args.batch, args.width, args.modes, args.res + args.pad
 plan = lib.get_plan(dev, (n, n), (m, m))
