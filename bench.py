@@ -176,7 +176,7 @@ class ClockSampler:
 class KernelTimer:
     """Wraps the fno_b200.lib call wrappers with CUDA events on the current stream."""
 
-    NAMES = ["fwd_transform", "inv_transform", "mix_fwd", "mix_bwd", "pointwise_fwd", "pointwise_wgrad", "pointwise_bwd",
+    NAMES = ["fwd_transform", "inv_transform", "layer_inv_fused", "mix_fwd", "mix_bwd", "pointwise_fwd", "pointwise_wgrad", "pointwise_bwd",
              "lift_stats", "lift_fwd", "lift_bwd", "head_fwd", "head_bwd"]
 
     def __init__(self, lib):
@@ -204,6 +204,11 @@ class KernelTimer:
                 tag = "inv_transform+bypass" + ("+gelu" if k.get("apply_gelu") else "") if k.get("addend") is not None else "inv_transform"
                 if k.get("s_out") is not None:
                     tag += "+preact"
+            if name == "layer_inv_fused":
+                # K3 + 1x1-conv bypass (+ bias, GELU, pre-activation store) in one tcgen05 kernel (+ its strided-axis
+                # pre-kernel): same algorithmic bytes as the r1 pair inv_transform(+addend) -- `lin` no longer exists
+                tag = "inv_transform+bypass" + ("+gelu" if k.get("apply_gelu") else "") + ("+preact" if k.get("s_out") is not None else "")
+                tag += " [tcgen05 fused]"
             if name == "pointwise_fwd" and k.get("transpose"):
                 tag = "pointwise_bwd_data"
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +260,7 @@ def algorithmic_bytes(tag: str, B: int) -> int:
         "head_fwd": 4 * B * RES * RES * (C + CFG["num_channels"]),
         "head_bwd": 4 * B * RES * RES * (C + CFG["num_channels"]) + act,
     }
-    return table[tag]
+    return table[tag.replace(" [tcgen05 fused]", "")]
 
 
 # ------------------------------------------------------------------------------------------------

@@ -23,13 +23,14 @@
 // "edge" warp computes them on the FP32 pipes, 32 rows at a time (lane = row), independently of the pipeline.
 //
 // Pipeline (per CTA, persistent over a contiguous range of rows; every hand-off is an mbarrier):
-//   2 B-prep warps   (one per row parity) bulk-copy raw T2 tiles into a 4-deep ring and    raw_full, mma_done -> b_ready
+//   2 B-prep warps   (one per row parity) bulk-copy raw T2 tiles into a 4-deep ring and    raw_full, mma_done -> ready
 //                    split them hi / lo into the operand buffers (the proxy fence this needs is why they are
 //                    separate warps: it is a MEMBAR that would wait for the converters' prefetched loads)
-//   8 converter warps  (lane quadrant x row parity) activation columns -> TMEM with wide     mma_done -> a_ready
+//   8 converter warps  (lane quadrant x row parity) activation columns -> TMEM with wide     mma_done -> ready
 //                    tcgen05.st, 2 own rows of loads in flight
-//   MMA warp         18 tcgen05.mma per row into a double-buffered accumulator         b_ready, a_ready, d_free -> mma_done
-//   8 epilogue warps tcgen05.ld, GELU, stores                                          mma_done -> d_free
+//   MMA warp         18 tcgen05.mma per row into a double-buffered accumulator         ready -> mma_done
+//   8 epilogue warps tcgen05.ld, GELU, stores                                          mma_done -> ready
+// (`ready[s]` collects the A buffer, the T2 operand tile and the free accumulator of a row: one wait in the MMA warp)
 #include <cuda.h>
 
 #include <cstdlib>
@@ -336,10 +337,9 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
   float* ostage = stage + (size_t)Cfg::CONV_WARPS * L2_PD * KA * 32;
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(
       (reinterpret_cast<size_t>(ostage + (TMA ? (size_t)4 * box_floats : 0)) + 15) & ~size_t(15));
-  unsigned long long* a_ready = bars;                  // [2] converters wrote A buffer s
+  unsigned long long* ready = bars;                    // [2] everything MMA(row) needs: A buffer s written (4 converter warps), T2
+                                                       //     operand tile s staged (1 B-prep warp), accumulator s read back (epilogue)
   unsigned long long* mma_done = bars + 2;             // [2] MMAs of the tile on buffers s complete (A / B free, D full)
-  unsigned long long* d_free = bars + 4;               // [2] accumulator s read back
-  unsigned long long* b_ready = bars + 6;              // [2] T2 operand tile s is split and staged
   unsigned long long* raw_full = bars + 8;             // [L2_NR] bulk copy of a raw T2 tile landed
   unsigned long long* f_ready = bars + 8 + L2_NR;      // [1] the twiddle columns of A are in tensor memory (once)
   unsigned long long* raw_free = bars + 9 + L2_NR;     // [L2_NR] the B-prep warp has read ring slot
@@ -361,10 +361,8 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(a_ready + s, 4);                     // the four lane-quadrant converter warps of parity s
-      mbar_init(mma_done + s, 1);
-      mbar_init(d_free + s, Cfg::EPI_WARPS);
-      mbar_init(b_ready + s, 1);
+      mbar_init(ready + s, 4 + 1 + Cfg::EPI_WARPS);  // ONE wait per row in the MMA warp: its serial instruction stream is
+      mbar_init(mma_done + s, 1);                    // the pipeline's critical path
     }
     for (int s = 0; s < L2_NR; ++s) mbar_init(raw_full + s, 1);
     mbar_init(f_ready, 4);
@@ -521,7 +519,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
       tmem_st_wait();                              // (no fence.proxy.async here: it compiles to MEMBAR.ALL.CTA, which would
       tc_fence_before();                           //  wait for this warp's copies in flight every row)
       __syncwarp();
-      if (lane == 0) mbar_arrive(a_ready + s);
+      if (lane == 0) mbar_arrive(ready + s);
       if (warp == 0) L2TR(5, it);
     };
 #pragma unroll
@@ -554,6 +552,10 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
     const int quad = ew & 3, e = ew >> 2;
     const int w = quad * 32 + lane;
     const bool wv = w < Wm;
+    if (lane == 0) {                               // both accumulators start out free
+      mbar_arrive(ready);
+      mbar_arrive(ready + 1);
+    }
     auto role = [&](auto Ec) {
       constexpr int E = decltype(Ec)::value;
       const int CPW = (C + Cfg::EW - 1) / Cfg::EW;
@@ -577,7 +579,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
         else { for (int i = 0; i < 16; ++i) v[i] = (float)i; }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(d_free + s);
+        if (lane == 0) mbar_arrive(ready + s);          // accumulator s is free for row it + 2
         if (ew == 0) L2TR(10, it);
         if (TMA) {
           // results -> dense [C][Wm] boxes in shared memory, one tensor-map store per row and tensor
@@ -633,20 +635,16 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
     const unsigned long long t2d = (unsigned long long)((t2_tile * 4) >> 4);       // descriptor step between T2 buffers
     const int nkq = KQ / 8;
     L2WAIT_HOT(f_ready, 0u);
+    unsigned row = (unsigned)t_begin - rsd.div((unsigned)t_begin) * RS;
     for (int it = 0; it < ntl; ++it) {
       const int s = it & 1;
       const unsigned ph = ((unsigned)it >> 1) & 1u;
       const unsigned td = tmem_base + TM_D + (unsigned)(s * NPAD);
       const unsigned long long d_th = d_t0 + (unsigned long long)(2 * s) * t2d, d_tl = d_th + t2d;
       const unsigned ab = tmem_base + TM_A + (unsigned)(s * 2 * KA);
-      unsigned fbase = tmem_base;
-      if (shift) {
-        const unsigned T = (unsigned)(t_begin + it);
-        const unsigned row = T - rsd.div(T) * RS;
-        if ((row * (unsigned)W) & 3u) fbase += TM_F1;
-      }
-      L2WAIT_HOT(d_free + s, ph ^ 1u);
-      L2WAIT_HOT(b_ready + s, ph);
+      const unsigned fbase = tmem_base + ((shift && ((row * (unsigned)W) & 3u)) ? TM_F1 : 0u);
+      if (++row == RS) row = 0;
+      L2WAIT_HOT(ready + s, ph);
       L2TR(6, it);
       tc_fence_after();
       __syncwarp();
@@ -662,10 +660,6 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
           tc_mma_tf32_ts_elect(td, fh, d_th + fo, idesc, single ? (unsigned)(ks != 0) : 1u);
         }
       }
-      L2WAIT_HOT(a_ready + s, ph);
-      L2TR(7, it);
-      tc_fence_after();
-      __syncwarp();
 #pragma unroll
       for (int ks = 0; ks < (L2DBG(4) ? 0 : KA / 8); ++ks) {
         const unsigned long long fo = (unsigned long long)(ks * 16);
@@ -715,7 +709,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(b_ready + s);
+      if (lane == 0) mbar_arrive(ready + s);
       if (j == 0) L2TR(14, it);
     }
   } else if (r_edge > 0 && !L2DBG(8)) {
@@ -1000,12 +994,14 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
     rc = launch_layer2d_t<24, 32, 2, 20>(args, st);
 #ifdef L2_TRACE
     static int calls = 0;
-    if (args.trace != nullptr && ++calls == 5) {
+    static const int dump_call = [] { const char* e = std::getenv("FNO_L2_TRACE_CALL"); return e ? std::atoi(e) : 5; }();
+    if (args.trace != nullptr && ++calls == dump_call) {
       unsigned long long h[64 * 16];
       cudaDeviceSynchronize();
       cudaMemcpy(h, args.trace, sizeof(h), cudaMemcpyDeviceToHost);
       const unsigned long long t0 = h[20 * 16 + 6];
       fprintf(stderr, "ev: 0 conv-wake 1 fenced 2 loads-in 3 sttm-issued 4 - 5 arrived | 6 mma-bready 7 mma-aready 8 committed | 9 epi-wake 10 epi-ld 11 epi-end | 12 bp-raw 13 bp-free 14 bp-arrived\n");
+      fprintf(stderr, "kernel span (CTA 0, rows 0..63): first ev6 %lld, row 63 ev8 %lld\n", (long long)(h[6] - t0), (long long)(h[63 * 16 + 8] - t0));
       for (int it = 20; it < 32; ++it) {
         fprintf(stderr, "tile %2d:", it);
         for (int e = 0; e < 15; ++e) fprintf(stderr, " %6lld", h[it * 16 + e] ? (long long)(h[it * 16 + e] - t0) : -1LL);
