@@ -195,69 +195,68 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
     }
     return;
   }
+  // one block = (sample, slice of row pairs, 8-channel row group): its part of every operand tile is a contiguous
+  // KQ * 32-byte segment, assembled in shared memory (zero padding included) and written out with 16-byte stores
+  extern __shared__ float4 hs4[];
+  float* hs = reinterpret_cast<float*>(hs4);
   const int q = threadIdx.x % m2, cl = threadIdx.x / m2;
   const int c = blockIdx.z * 8 + cl;
-  if (cl >= 8) return;
+  const bool active = cl < 8 && c < C;
   const int bd = blockIdx.x;                  // b * D1 + d1
-  if (c >= C) {
-    // rows of the last 8-row group beyond the width: zeros (the operand tile is consumed whole)
-    const int NPz = H / 2 + 1;
-    const int tz0 = blockIdx.y * TL, tz1 = (tz0 + TL < NPz) ? tz0 + TL : NPz;
-    const int eo = (c >> 3) * KQ * 8 + (c & 7) * 4;
-    float* __restrict__ bz = T2g + (size_t)bd * H * tile_floats;
-    for (int t = tz0; t < tz1; ++t)
-      for (int k = q; k < KQ; k += m2) {
-        bz[(size_t)t * tile_floats + eo + (k >> 2) * 32 + (k & 3)] = 0.f;
-        if (t != 0 && 2 * t != H) bz[(size_t)(H - t) * tile_floats + eo + (k >> 2) * 32 + (k & 3)] = 0.f;
-      }
-    return;
-  }
-  const int b = bd / D1, d1 = bd - b * D1;
-  const size_t plane = ((size_t)b * C + c) * D1 + d1;
-  const float2* __restrict__ Yp = Y + plane * (size_t)(2 * m1) * m2 + q;
-  float PR[M1T + 1], PI[M1T + 1], MR[M1T + 1], MI[M1T + 1];
-  const float2 y0 = __ldg(Yp);
-#pragma unroll
-  for (int j = 1; j <= M1T; ++j) {
-    float2 yp = make_float2(0.f, 0.f), yn = make_float2(0.f, 0.f);
-    if (j < m1) yp = __ldg(Yp + (size_t)j * m2);
-    if (j <= m1) yn = __ldg(Yp + (size_t)(2 * m1 - j) * m2);
-    PR[j] = yp.x + yn.x; PI[j] = yp.y + yn.y;
-    MR[j] = yp.x - yn.x; MI[j] = yp.y - yn.y;
-  }
-  float sc = scale;
-  if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
   const int NP = H / 2 + 1;
   const int t0 = blockIdx.y * TL, t1 = (t0 + TL < NP) ? t0 + TL : NP;
-  const int eoff = (c >> 3) * KQ * 8 + (c & 7) * 4;
-  const int o_re = eoff + (q >> 2) * 32 + (q & 3), o_im = eoff + ((m2 + q) >> 2) * 32 + ((m2 + q) & 3);
-  float* __restrict__ base = T2g + (size_t)bd * H * tile_floats;
-  for (int t = t0; t < t1; ++t) {
-    const float4* __restrict__ r4 = reinterpret_cast<const float4*>(twH + (size_t)t * JP);
-    float tw[JP];
-#pragma unroll
-    for (int i = 0; i < JP / 4; ++i) {
-      const float4 v = __ldg(r4 + i);
-      tw[4 * i] = v.x; tw[4 * i + 1] = v.y; tw[4 * i + 2] = v.z; tw[4 * i + 3] = v.w;
-    }
-    float er = y0.x, ei = y0.y, odr = 0.f, odi = 0.f;
+  const int seg = KQ * 8;                     // floats of one (row, row group) segment
+  for (int i = threadIdx.x; i < 2 * TL * seg / 4; i += blockDim.x) hs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  if (active) {
+    const int b = bd / D1, d1 = bd - b * D1;
+    const size_t plane = ((size_t)b * C + c) * D1 + d1;
+    const float2* __restrict__ Yp = Y + plane * (size_t)(2 * m1) * m2 + q;
+    float PR[M1T + 1], PI[M1T + 1], MR[M1T + 1], MI[M1T + 1];
+    const float2 y0 = __ldg(Yp);
 #pragma unroll
     for (int j = 1; j <= M1T; ++j) {
-      er = fmaf(PR[j], tw[j], er);
-      ei = fmaf(PI[j], tw[j], ei);
-      odr = fmaf(MI[j], tw[M1T + j], odr);
-      odi = fmaf(MR[j], tw[M1T + j], odi);
+      float2 yp = make_float2(0.f, 0.f), yn = make_float2(0.f, 0.f);
+      if (j < m1) yp = __ldg(Yp + (size_t)j * m2);
+      if (j <= m1) yn = __ldg(Yp + (size_t)(2 * m1 - j) * m2);
+      PR[j] = yp.x + yn.x; PI[j] = yp.y + yn.y;
+      MR[j] = yp.x - yn.x; MI[j] = yp.y - yn.y;
     }
-    float* __restrict__ o = base + (size_t)t * tile_floats;
-    o[o_re] = sc * (er - odr);
-    o[o_im] = -sc * (ei + odi);
-    for (int k = 2 * m2 + q; k < KQ; k += m2) o[eoff + (k >> 2) * 32 + (k & 3)] = 0.f;      // K padding
-    if (t != 0 && 2 * t != H) {
-      float* __restrict__ o2 = base + (size_t)(H - t) * tile_floats;
-      o2[o_re] = sc * (er + odr);
-      o2[o_im] = -sc * (ei - odi);
-      for (int k = 2 * m2 + q; k < KQ; k += m2) o2[eoff + (k >> 2) * 32 + (k & 3)] = 0.f;
+    float sc = scale;
+    if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
+    const int o_re = (q >> 2) * 32 + cl * 4 + (q & 3), o_im = ((m2 + q) >> 2) * 32 + cl * 4 + ((m2 + q) & 3);
+    for (int t = t0; t < t1; ++t) {
+      const float4* __restrict__ r4 = reinterpret_cast<const float4*>(twH + (size_t)t * JP);
+      float tw[JP];
+#pragma unroll
+      for (int i = 0; i < JP / 4; ++i) {
+        const float4 v = __ldg(r4 + i);
+        tw[4 * i] = v.x; tw[4 * i + 1] = v.y; tw[4 * i + 2] = v.z; tw[4 * i + 3] = v.w;
+      }
+      float er = y0.x, ei = y0.y, odr = 0.f, odi = 0.f;
+#pragma unroll
+      for (int j = 1; j <= M1T; ++j) {
+        er = fmaf(PR[j], tw[j], er);
+        ei = fmaf(PI[j], tw[j], ei);
+        odr = fmaf(MI[j], tw[M1T + j], odr);
+        odi = fmaf(MR[j], tw[M1T + j], odi);
+      }
+      float* __restrict__ o = hs + (size_t)(2 * (t - t0)) * seg;       // row t, then its mirror H - t
+      o[o_re] = sc * (er - odr);
+      o[o_im] = -sc * (ei + odi);
+      o[seg + o_re] = sc * (er + odr);
+      o[seg + o_im] = -sc * (ei - odi);
     }
+  }
+  __syncthreads();
+  float* __restrict__ base = T2g + (size_t)bd * H * tile_floats + (size_t)blockIdx.z * seg;
+  const int seg4 = seg / 4;
+  for (int i = threadIdx.x; i < 2 * (t1 - t0) * seg4; i += blockDim.x) {
+    const int slot = i / seg4, f = i - slot * seg4;
+    const int t = t0 + (slot >> 1);
+    if ((slot & 1) && (t == 0 || 2 * t == H)) continue;               // self-paired rows have no mirror
+    const int row = (slot & 1) ? H - t : t;
+    reinterpret_cast<float4*>(base + (size_t)row * tile_floats)[f] = hs4[i];
   }
 }
 
@@ -905,7 +904,9 @@ int launch_hinv_t(const Plan* p, const float* Y, float* T2g, int B, int C, int K
   TS = (NP + TL - 1) / TL;
   // one more z-slice of blocks computes the spectral part of the edge columns (W > 128) in the same launch
   dim3 grid((unsigned)(B * p->D1), (unsigned)TS, (unsigned)((C + 7) / 8 + (ea.r_edge > 0 ? 1 : 0)));
-  hinv_tiles_kernel<M1T><<<grid, threads, 0, st>>>(reinterpret_cast<const float2*>(Y), T2g, p->twH, p->H, p->W, p->m1, p->m2,
+  const size_t smem = sizeof(float) * 2ul * TL * KQ * 8;
+  if (smem > 48 * 1024) { set_error("hinv_tiles: row slice too large"); return FNO_E_ARG; }
+  hinv_tiles_kernel<M1T><<<grid, threads, smem, st>>>(reinterpret_cast<const float2*>(Y), T2g, p->twH, p->H, p->W, p->m1, p->m2,
                                                   C, p->D1, KQ, tile_floats, TL, cmode, scale, ea);
   count_launch();
   return check_launch("hinv_tiles_kernel");
