@@ -237,11 +237,16 @@ int fno_nrmse_bwd(const float* out, const float* target, const void* work, const
  * clip_value = max(hparams[7], hparams[8] * total_norm), clip_grad_norm_ coefficient, then
  * Adam with coupled L2 weight decay and (if hparams[2] = T_max > 0) the CosineAnnealingLR value of
  * this step, all driven by the device-resident step counter state[0].
- *   chunks   device array of { float* p; const float* g; float* m; float* v; int n; int pad; }
- *            (fno_opt_chunk_bytes() each, n <= fno_opt_chunk_floats()); complex tensors as real pairs
+ *   chunks   device array of { float* p; const float* g; float* m; float* v; int n; float lr0; }
+ *            (fno_opt_chunk_bytes() each, n <= fno_opt_chunk_floats()); complex tensors as real pairs; lr0 = base
+ *            learning rate of the chunk's parameter group (0 = hparams[0]): the three Adam groups of the joint loop
+ *            (fno_aux/fno_train_aux.py:175-179) share one schedule factor
  *   partials device scratch, nchunks floats
  *   state    device float[8]: step, total_norm, clip_coef, lr, 1-beta1^t, 1-beta2^t, clip_value, clipped_norm
- *   hparams  device float[9]: lr0, eta_min, T_max, beta1, beta2, eps, weight_decay, clip_floor, clip_frac */
+ *   hparams  device float[12]: lr0, eta_min, T_max, beta1, beta2, eps, weight_decay, clip_floor, clip_frac,
+ *            sched_extra = scheduler steps taken besides the one per optimizer step (fno/train.py:340 steps the
+ *            CosineAnnealingLR once more per epoch), 1 - beta1 and 1 - beta2 evaluated in double, then rounded
+ *            (what torch.optim.Adam multiplies by; 1.0f - 0.999f differs from it by 1.3e-5)                */
 int fno_opt_chunk_floats(void);
 size_t fno_opt_chunk_bytes(void);
 int fno_clip_adam_step(const void* chunks, int nchunks, float* partials, float* state,

@@ -37,6 +37,16 @@ struct Plan {
   int tc_nch;
 };
 
+// One-time setup that must run once PER DEVICE: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the current
+// device only, so a process-wide flag would leave the second GPU of a single-process multi-GPU program without it.
+struct PerDeviceOnce {
+  std::atomic<int> done[64];
+  PerDeviceOnce() { for (auto& d : done) d.store(0); }
+  static int current() { int d = 0; return cudaGetDevice(&d) == cudaSuccess ? d : -1; }
+  bool need() const { const int d = current(); return d < 0 || d >= 64 || !done[d].load(); }
+  void mark() { const int d = current(); if (d >= 0 && d < 64) done[d].store(1); }
+};
+
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
 extern std::atomic<unsigned long long> g_launches;

@@ -542,12 +542,12 @@ extern "C" int fno_head_bwd_tc(const float* h, const float* dout, const float* W
   if (total > 0x7fffffffL) { set_error("fno_head_bwd_tc: too many tiles"); return FNO_E_ARG; }
   g.by_w.init((unsigned)W_in);
   g.by_tps.init((unsigned)tps);
-  static std::atomic<int> done{0};
-  if (!done.load()) {
+  static PerDeviceOnce done;
+  if (done.need()) {
     if (cudaFuncSetAttribute(head_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(head_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_bwd_tc)");
-    done.store(1);
+    done.mark();
   }
   const int ctas = (int)(total < 148 ? total : 148);
   float* rec = static_cast<float*>(work);

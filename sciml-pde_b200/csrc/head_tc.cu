@@ -271,12 +271,12 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
   if (total > 0x7fffffffL) { set_error("fno_head_fwd_tc: too many tiles"); return FNO_E_ARG; }
   const size_t smem = 4 * A_BYTES + 2 * B_BYTES + sizeof(float) * (TC_HID * TC_VP + TC_HID + 8 * TC_M * TC_VP) +
                       6 * sizeof(unsigned long long) + 16;
-  static std::atomic<int> done{0};
-  if (!done.load()) {
+  static PerDeviceOnce done;
+  if (done.need()) {
     if (cudaFuncSetAttribute(head_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(head_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_fwd_tc)");
-    done.store(1);
+    done.mark();
   }
   const int ctas = (int)(total < 148 ? total : 148);
   const int single = g_math_mode.load() == FNO_MATH_TF32;

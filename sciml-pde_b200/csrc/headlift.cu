@@ -844,11 +844,11 @@ int launch_head_fwd(const float* h, const float* W1, const float* b1, const floa
                     const float* stats, float* out, const PixGeo& g, int B, int C, int HID, int V, cudaStream_t st) {
   const size_t smem = sizeof(float) * ((size_t)HID * CP + (size_t)HID * VP + HID);
   auto k = head_fwd_kernel<CP, VP>;
-  static std::atomic<int> done{0};
-  if (!done.load()) {
+  static PerDeviceOnce done;
+  if (done.need()) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_fwd)");
-    done.store(1);
+    done.mark();
   }
   if (smem > 160 * 1024) { set_error("head_fwd: hidden %d x width %d too large", HID, C); return FNO_E_ARG; }
   dim3 grid((unsigned)((g.npix + 2 * HF_THREADS - 1) / (2 * HF_THREADS)), B);
@@ -863,11 +863,11 @@ int launch_head_bwd(const float* h, const float* dout, const float* W1, const fl
                     const PixGeo& g, int B, int C, int HID, int V, cudaStream_t st) {
   const size_t smem = head_bwd_smem<CP, VP>(HID);
   auto k = head_bwd_kernel<CP, VP>;
-  static std::atomic<int> done{0};
-  if (!done.load()) {
+  static PerDeviceOnce done;
+  if (done.need()) {
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_bwd)");
-    done.store(1);
+    done.mark();
   }
   if (smem > 227 * 1024) { set_error("head_bwd: hidden %d x width %d too large", HID, C); return FNO_E_ARG; }
   const TileMap tm = make_tiles(g, B);
@@ -1025,12 +1025,12 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
       const size_t red_bytes = sizeof(float) * (size_t)(LB2_THREADS / 32) * nitems * 16;
       const size_t smem2 = tile_bytes > red_bytes ? tile_bytes : red_bytes;
       const int ctas = tm0.total < LB_CTAS ? tm0.total : LB_CTAS;
-      static std::atomic<int> done2{0};
-      if (!done2.load()) {
+      static PerDeviceOnce done2;
+      if (done2.need()) {
         if (cudaFuncSetAttribute(lift_bwd2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess ||
             cudaFuncSetAttribute(lift_bwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
           return check_launch("cudaFuncSetAttribute(lift_bwd2)");
-        done2.store(1);
+        done2.mark();
       }
       if (smem2 <= 64 * 1024) {
         if (NIT == 1) lift_bwd2_kernel<1><<<ctas, LB2_THREADS, smem2, st>>>(x, grid, stats, dh, part0, g, tm0, T, V, G, C);
@@ -1050,11 +1050,11 @@ extern "C" int fno_lift_bwd(const float* x, const float* grid, const float* stat
     }
   }
   const size_t smem = sizeof(float) * ((size_t)C * TP + (size_t)FQ * 4 * TP);
-  static std::atomic<int> done{0};
-  if (!done.load()) {
+  static PerDeviceOnce done;
+  if (done.need()) {
     if (cudaFuncSetAttribute(lift_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(lift_bwd)");
-    done.store(1);
+    done.mark();
   }
   if (smem > 160 * 1024) { set_error("fno_lift_bwd: tile does not fit shared memory"); return FNO_E_ARG; }
   const TileMap tm = make_tiles(g, B);

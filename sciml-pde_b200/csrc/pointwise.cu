@@ -541,12 +541,12 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
   const int ygroups = (ntiles + warps - 1) / warps;
   const size_t smem = sizeof(float) * 2ul * (size_t)(Co + Ci) * KT;
   if (smem > 200 * 1024) { set_error("fno_pointwise_wgrad: width %d too large", Co + Ci); return FNO_E_ARG; }
-  static std::atomic<int> attr_done{0};
-  if (!attr_done.load()) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     if (cudaFuncSetAttribute(wgrad_partial_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
         cudaSuccess)
       return check_launch("cudaFuncSetAttribute(wgrad)");
-    attr_done.store(1);
+    attr_done.mark();
   }
   const int slabs_per_sample = (int)((N + KT - 1) / KT);
   const long total_slabs = (long)B * slabs_per_sample;
@@ -559,14 +559,14 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
   // v2 (TMA bulk-fed): persistent CTAs, one per SM, each over a contiguous range of 512-pixel slabs
   const size_t smem2 = sizeof(float) * (size_t)WG2_STAGES * (Co + Ci) * WG2_KT + 2 * WG2_STAGES * sizeof(unsigned long long);
   if (aligned && smem2 <= 200 * 1024 && ntiles <= WG2_MAXW) {
-    static std::atomic<int> attr2_done{0};
-    if (!attr2_done.load()) {
+    static PerDeviceOnce attr2_done;
+    if (attr2_done.need()) {
       if (cudaFuncSetAttribute(wgrad2_partial_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
               cudaSuccess ||
           cudaFuncSetAttribute(wgrad2_partial_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
               cudaSuccess)
         return check_launch("cudaFuncSetAttribute(wgrad2)");
-      attr2_done.store(1);
+      attr2_done.mark();
     }
     const int KH = (2 * ntiles <= WG2_MAXW) ? 2 : 1;       // pixel halves per tile
     const int warps2 = ntiles * KH;

@@ -113,13 +113,13 @@ nrmse_grad_kernel(const float* __restrict__ out, const float* __restrict__ tgt, 
 constexpr int OPT_CHUNK = 4096;     // floats per chunk (one CTA)
 constexpr int OPT_THREADS = 256;
 
-struct OptChunk {                   // 48 bytes; built once on the host, lives in device memory
+struct OptChunk {                   // 40 bytes; built once on the host, lives in device memory
   float* p;
   const float* g;
   float* m;
   float* v;
   int n;
-  int pad;
+  float lr0;                        // base learning rate of the chunk's parameter group (0: hparams[0])
 };
 
 __global__ void __launch_bounds__(OPT_THREADS)
@@ -145,7 +145,9 @@ sqnorm_partial_kernel(const OptChunk* __restrict__ chunks, float* __restrict__ p
 
 // state[0] = step count (as float, exact up to 2^24), [1] = total_norm, [2] = clip coefficient,
 // [3] = lr of this step, [4] = 1 - beta1^t, [5] = 1 - beta2^t, [6] = clip_value, [7] = clipped norm
-// hp: lr0, eta_min, T_max (<= 0: constant lr), beta1, beta2, eps, weight_decay, clip_floor, clip_frac
+// hp: lr0, eta_min, T_max (<= 0: constant lr), beta1, beta2, eps, weight_decay, clip_floor, clip_frac,
+//     sched_extra (scheduler steps taken in addition to one per optimizer step: the reference steps its
+//     CosineAnnealingLR once more per epoch, fno/train.py:340), 1 - beta1, 1 - beta2 (rounded from double)
 __global__ void __launch_bounds__(256)
 opt_prepare_kernel(const float* __restrict__ part, int nparts, float* __restrict__ state, const float* __restrict__ hp) {
   __shared__ double red[256];
@@ -165,7 +167,8 @@ opt_prepare_kernel(const float* __restrict__ part, int nparts, float* __restrict
   const double t_prev = (double)state[0];      // scheduler steps taken so far = optimizer steps so far
   const double t = t_prev + 1.0;
   double lr = (double)hp[0];
-  if (hp[2] > 0.f) lr = (double)hp[1] + ((double)hp[0] - (double)hp[1]) * 0.5 * (1.0 + cos(M_PI * t_prev / (double)hp[2]));
+  if (hp[2] > 0.f)
+    lr = (double)hp[1] + ((double)hp[0] - (double)hp[1]) * 0.5 * (1.0 + cos(M_PI * (t_prev + (double)hp[9]) / (double)hp[2]));
   state[0] = (float)t;
   state[1] = (float)total;
   state[2] = (float)coef;
@@ -179,16 +182,22 @@ opt_prepare_kernel(const float* __restrict__ part, int nparts, float* __restrict
 __global__ void __launch_bounds__(OPT_THREADS)
 adam_apply_kernel(const OptChunk* __restrict__ chunks, const float* __restrict__ state, const float* __restrict__ hp) {
   const OptChunk c = chunks[blockIdx.x];
-  const float coef = state[2], lr = state[3], bc1 = state[4], bc2 = state[5];
+  const float coef = state[2], bc1 = state[4], bc2 = state[5];
   const float b1 = hp[3], b2 = hp[4], eps = hp[5], wd = hp[6];
+  // 1 - beta as torch has it: evaluated in double from the Python floats, THEN rounded (1.0f - 0.999f is off by 1.3e-5)
+  const float omb1 = hp[10], omb2 = hp[11];
+  // parameter groups differ in their base lr only (fno_aux/fno_train_aux.py:175-179); the schedule factor is shared:
+  // lr_g = eta_min + (lr0_g - eta_min) * (lr - eta_min) / (lr0 - eta_min)
+  float lr = state[3];
+  if (c.lr0 > 0.f && c.lr0 != hp[0]) lr = (hp[0] != hp[1]) ? hp[1] + (c.lr0 - hp[1]) * ((lr - hp[1]) / (hp[0] - hp[1])) : c.lr0;
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   for (int i = threadIdx.x; i < c.n; i += OPT_THREADS) {
     const float p = c.p[i];
     float g = __ldg(c.g + i) * coef;
     g = fmaf(wd, p, g);                               // Adam(weight_decay): coupled L2
-    const float m = fmaf(b1, c.m[i], (1.0f - b1) * g);
-    const float v = fmaf(b2, c.v[i], (1.0f - b2) * g * g);
+    const float m = fmaf(b1, c.m[i], omb1 * g);
+    const float v = fmaf(b2, c.v[i], omb2 * g * g);
     c.m[i] = m;
     c.v[i] = v;
     const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;

@@ -920,11 +920,11 @@ int launch_fwd_t(const Plan* p, const float* x, const float* preact, float* ds_o
     return FNO_OK;
   }
   if (MINB == 3) {   // experimental class: opt in to large dynamic shared memory on first use
-    static std::atomic<int> done3{0};
-    if (!done3.load()) {
+    static PerDeviceOnce done3;
+    if (done3.need()) {
       cudaFuncSetAttribute(k0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
       cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
-      done3.store(1);
+      done3.mark();
     }
   }
   const int G = G_launch;
@@ -950,10 +950,10 @@ int launch_inv_t(const Plan* p, const float* Y, const float* addend, float* s_ou
     return FNO_OK;
   }
   if (MINB == 3) {
-    static std::atomic<int> done3{0};
-    if (!done3.load()) {
+    static PerDeviceOnce done3;
+    if (done3.need()) {
       cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmemC);
-      done3.store(1);
+      done3.mark();
     }
   }
   const int G = G_launch;

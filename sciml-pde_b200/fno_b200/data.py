@@ -109,6 +109,29 @@ def epoch_indices(n_items: int, batch: int, shuffle: bool, seed: int, epoch: int
     return [order[s:s + batch][rank::world].contiguous() for s in range(0, n_items, batch)]
 
 
+def epoch_plan(n_items: int, batch: int, shuffle: bool, seed: int, epoch: int = 0, rank: int = 0, world: int = 1):
+    """``epoch_indices`` made safe for data parallelism: EVERY rank gets a non-empty batch for EVERY step (so the
+    gradient all-reduces pair up), together with the weight its mean loss must be multiplied by so that the averaged
+    gradient is the gradient of the GLOBAL batch mean (the reference's DataLoader has ``drop_last=False``,
+    fno/train.py:95-97, so the last global batch is ragged: ranks hold unequal, possibly empty, slices).
+
+    Returns [(items, weight)]: weight = local_b * world / global_b; a rank whose slice of a ragged tail is empty gets the
+    first item of that global batch with weight 0 (its gradient contributes nothing, every hook still fires)."""
+    out = []
+    plans = [epoch_indices(n_items, batch, shuffle, seed, epoch, r, world) for r in range(world)] if world > 1 else None
+    mine = epoch_indices(n_items, batch, shuffle, seed, epoch, rank, world)
+    for step, items in enumerate(mine):
+        if world == 1:
+            out.append((items, 1.0))
+            continue
+        global_b = sum(int(pl[step].numel()) for pl in plans)
+        if items.numel() == 0:
+            out.append((plans[0][step][:1].clone(), 0.0))
+        else:
+            out.append((items, items.numel() * world / global_b))
+    return out
+
+
 class DeviceWindows:
     """Trajectories cached on the GPU, sliding windows gathered on the device (one copy kernel per batch).
 
@@ -155,8 +178,13 @@ class DeviceWindows:
         yy = yy.view((B,) + self.spatial + (self.rollout, self.V))
         return xx, yy, self.grid.unsqueeze(0).expand(B, *([-1] * (self.nd + 1)))
 
-    def epoch(self, batch: int, shuffle: bool = True, seed: int = 16, epoch: int = 0, rank: int = 0, world: int = 1):
-        """Iterates this rank's batches of one epoch (see ``epoch_indices``)."""
-        for items in epoch_indices(len(self), batch, shuffle, seed, epoch, rank, world):
-            if items.numel():
-                yield self.batch(items)
+    def epoch(self, batch: int, shuffle: bool = True, seed: int = 16, epoch: int = 0, rank: int = 0, world: int = 1,
+              with_weight: bool = False):
+        """Iterates this rank's batches of one epoch (see ``epoch_plan``).  Under data parallelism every rank yields a
+        batch for every step; ``with_weight=True`` appends the loss weight of ``epoch_plan`` (pass it to the train
+        step: ``step(xx, yy, grid, weight=w)``) -- required whenever ``len(self) % (batch * world) != 0``."""
+        for items, w in epoch_plan(len(self), batch, shuffle, seed, epoch, rank, world):
+            if world > 1 and not with_weight and w != 1.0:
+                raise ValueError("DeviceWindows.epoch: ragged global batch under data parallelism -- iterate with "
+                                 "with_weight=True and pass the weight to the train step")
+            yield (self.batch(items) + (w,)) if with_weight else self.batch(items)

@@ -132,6 +132,34 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Runs a wrapper with the CUDA device of its first tensor argument current: the launch then goes to that device's
+    current stream, per-device kernel attributes apply to the right context, and a plan created for another device is
+    refused instead of being launched with foreign pointers (single-process multi-GPU use)."""
+    import functools
+
+    @functools.wraps(fn)
+    def inner(*args, **kwargs):
+        dev = None
+        plan = None
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, Plan) and plan is None:
+                plan = a
+            elif isinstance(a, torch.Tensor) and a.is_cuda and dev is None:
+                dev = a.device
+            elif isinstance(a, (list, tuple)) and dev is None and a and isinstance(a[0], torch.Tensor) and a[0].is_cuda:
+                dev = a[0].device
+        if dev is None:
+            return fn(*args, **kwargs)
+        if plan is not None and plan.device != dev.index:
+            raise FnoError(f"plan was created for cuda:{plan.device}, tensors live on {dev}")
+        if dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return inner
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -222,6 +250,7 @@ def shutdown():
 # ---------------------------------------------------------------------------------------------
 # thin call wrappers (shape bookkeeping only)
 # ---------------------------------------------------------------------------------------------
+@_on_tensor_device
 def fwd_transform(plan: Plan, x: torch.Tensor, *, preact: Optional[torch.Tensor] = None,
                   ds_out: Optional[torch.Tensor] = None, cmode: int = 0, scale: float = 1.0) -> torch.Tensor:
     """x [B, C, *spatial] f32 -> retained spectrum [B, C, *spec_shape] complex64."""
@@ -252,6 +281,7 @@ def fwd_transform(plan: Plan, x: torch.Tensor, *, preact: Optional[torch.Tensor]
     return X
 
 
+@_on_tensor_device
 def inv_transform(plan: Plan, Y: torch.Tensor, *, addend: Optional[torch.Tensor] = None,
                   s_out: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, cmode: int = 1,
                   scale: Optional[float] = None, apply_gelu: bool = False) -> torch.Tensor:
@@ -291,6 +321,7 @@ def layer_fused_supported(plan: Plan, width: int) -> bool:
     return bool(LAYER_TENSOR_CORES and plan.nd == 2 and load().fno_layer2d_fused_supported(plan.handle, int(width)))
 
 
+@_on_tensor_device
 def layer_inv_fused(plan: Plan, Y: torch.Tensor, a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *,
                     s_out: Optional[torch.Tensor] = None, cmode: int = 1, scale: Optional[float] = None,
                     apply_gelu: bool = False, transpose: bool = False) -> torch.Tensor:
@@ -330,6 +361,7 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
     return arr
 
 
+@_on_tensor_device
 def mix_fwd(plan: Plan, X: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
     _require(X, torch.complex64, "X")
     B, Ci = X.shape[0], X.shape[1]
@@ -344,6 +376,7 @@ def mix_fwd(plan: Plan, X: torch.Tensor, weights: Sequence[torch.Tensor]) -> tor
     return Y
 
 
+@_on_tensor_device
 def mix_bwd(plan: Plan, X: Optional[torch.Tensor], gY: torch.Tensor, weights: Sequence[torch.Tensor], *,
             need_gx: bool = True, need_gw: bool = True):
     _require(gY, torch.complex64, "gY")
@@ -359,6 +392,7 @@ def mix_bwd(plan: Plan, X: Optional[torch.Tensor], gY: torch.Tensor, weights: Se
     return gX, gws
 
 
+@_on_tensor_device
 def pointwise_fwd(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, transpose: bool = False,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """1x1 conv on channel-first [B, C, *spatial]; weight is the conv weight [Co, Ci, 1, 1(, 1)]."""
@@ -380,6 +414,7 @@ def pointwise_fwd(a: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Te
     return out
 
 
+@_on_tensor_device
 def pointwise_wgrad_buffers(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True):
     """Allocates (gw, gb, work) for pointwise_wgrad on the CURRENT stream (so that the launch itself
     may run on a side stream without handing the caching allocator cross-stream blocks)."""
@@ -392,6 +427,7 @@ def pointwise_wgrad_buffers(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, 
     return gw, gb, work
 
 
+@_on_tensor_device
 def pointwise_bwd(ds: torch.Tensor, a: torch.Tensor, weight: torch.Tensor, *, need_bias: bool = True):
     """Autograd of the 1x1 convolution in one call: (dx = W^T ds, gW, gb).  ds is read once when the TMA-fed
     weight-gradient kernel can carry the data gradient (fno_pointwise_bwd)."""
@@ -407,6 +443,7 @@ def pointwise_bwd(ds: torch.Tensor, a: torch.Tensor, weight: torch.Tensor, *, ne
     return dx, gw, gb
 
 
+@_on_tensor_device
 def pointwise_wgrad(ds: torch.Tensor, a: torch.Tensor, weight_shape, *, need_bias: bool = True, buffers=None):
     _require(ds, torch.float32, "ds")
     _require(a, torch.float32, "a")
@@ -451,6 +488,7 @@ class TrunkGeo:
         return self.R_in, self.W_in, self.R_out, self.Wp
 
 
+@_on_tensor_device
 def lift_stats(x: torch.Tensor) -> torch.Tensor:
     """x [B, *spatial, T, V] -> [B, 2, V] (mean, std + 1e-7) over everything but batch and variable."""
     _require(x, torch.float32, "x")
@@ -464,6 +502,7 @@ def lift_stats(x: torch.Tensor) -> torch.Tensor:
     return stats
 
 
+@_on_tensor_device
 def lift_fwd(geo: TrunkGeo, x, grid, stats, W0, b0) -> torch.Tensor:
     for t, n in ((x, "x"), (grid, "grid"), (stats, "stats"), (W0, "fc0.weight"), (b0, "fc0.bias")):
         _require(t, torch.float32, n)
@@ -476,6 +515,7 @@ def lift_fwd(geo: TrunkGeo, x, grid, stats, W0, b0) -> torch.Tensor:
     return h
 
 
+@_on_tensor_device
 def lift_bwd(geo: TrunkGeo, x, grid, stats, dh, W0_shape):
     _require(dh, torch.float32, "dh")
     B, T, V, G, C = x.shape[0], x.shape[-2], x.shape[-1], grid.shape[-1], W0_shape[0]
@@ -506,6 +546,7 @@ def get_math_mode() -> str:
     return {v: k for k, v in MATH_MODES.items()}[load().fno_get_math_mode()]
 
 
+@_on_tensor_device
 def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
     for t, n in ((h, "h"), (W1, "fc1.weight"), (b1, "fc1.bias"), (W2, "fc2.weight"), (b2, "fc2.bias"),
                  (stats, "stats")):
@@ -525,6 +566,7 @@ def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
     return out
 
 
+@_on_tensor_device
 def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
     _require(dout, torch.float32, "dout")
     B, C, HID, V = h.shape[0], h.shape[1], W1.shape[0], W2.shape[0]
@@ -542,6 +584,7 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
     return dh, gW1, gb1, gW2, gb2
 
 
+@_on_tensor_device
 def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Tensor, initial_step: int, rollout: int):
     """traj [n_traj, pixels, T, V] (device, time-inner) -> xx [B, pixels, initial_step, V], yy [B, pixels, rollout, V]
     for the items (traj_idx[b], t_start[b]); one copy kernel, nothing touches the host."""

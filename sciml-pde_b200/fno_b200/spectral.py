@@ -63,20 +63,42 @@ class SpectralConv3d(_SpectralConvBase):
         return _corner_mix(input, weights)
 
 
+class _CornerMixFn(torch.autograd.Function):
+    """einsum('bi...,io...->bo...') for ONE corner block through the K2 kernels (forward: fno_mix_fwd, backward:
+    fno_mix_bwd), differentiable like the reference's einsum (fno.py:66-68, :255-257).  The block is presented as
+    the low corner of a plan whose other corners are multiplied by zeros."""
+
+    @staticmethod
+    def _embed(inp, w):
+        modes = tuple(w.shape[2:])
+        nd = len(modes)
+        spatial = tuple(2 * m for m in modes[:-1]) + (2 * (modes[-1] - 1) + 2,)
+        plan = lib.get_plan(inp.device, spatial, modes)
+        sl = (slice(None), slice(None)) + tuple(slice(0, m) for m in modes)
+        zeros = torch.zeros_like(w)
+        ws = [w.contiguous()] + [zeros] * ((2 if nd == 2 else 4) - 1)
+        return plan, sl, ws
+
+    @staticmethod
+    def forward(ctx, inp, w):
+        plan, sl, ws = _CornerMixFn._embed(inp, w)
+        X = torch.zeros(tuple(inp.shape[:2]) + plan.spec_shape, dtype=torch.complex64, device=inp.device)
+        X[sl] = inp
+        Y = lib.mix_fwd(plan, X, ws)
+        ctx.save_for_backward(X, w)
+        return Y[sl].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        X, w = ctx.saved_tensors
+        plan, sl, ws = _CornerMixFn._embed(X, w)
+        gY = torch.zeros((g.shape[0], w.shape[1]) + plan.spec_shape, dtype=torch.complex64, device=g.device)
+        gY[sl] = g
+        gX, gws = lib.mix_bwd(plan, X, gY, ws, need_gx=ctx.needs_input_grad[0], need_gw=ctx.needs_input_grad[1])
+        return (gX[sl].contiguous() if gX is not None else None), (gws[0] if gws is not None else None)
+
+
 def _corner_mix(inp: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
-    """einsum('bi...,io...->bo...') for ONE corner block through the K2 kernel: the block is
-    presented as the low corner of a plan whose other corners are multiplied by zeros."""
     if not inp.is_cuda:
         raise lib.FnoError("compl_mul runs on CUDA sm_100a only")
-    modes = tuple(w.shape[2:])
-    nd = len(modes)
-    spatial = tuple(2 * m for m in modes[:-1]) + (2 * (modes[-1] - 1) + 2,)
-    plan = lib.get_plan(inp.device, spatial, modes)
-    B, Ci = inp.shape[:2]
-    X = torch.zeros((B, Ci) + plan.spec_shape, dtype=torch.complex64, device=inp.device)
-    sl = (slice(None), slice(None)) + tuple(slice(0, m) for m in modes)
-    X[sl] = inp
-    zeros = torch.zeros_like(w)
-    ws = [w.contiguous()] + [zeros] * ((2 if nd == 2 else 4) - 1)
-    Y = lib.mix_fwd(plan, X, ws)
-    return Y[sl].contiguous()
+    return _CornerMixFn.apply(inp, w)

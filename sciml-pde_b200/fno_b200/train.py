@@ -60,9 +60,11 @@ class TrainStep:
             self.scheduler.step()
         return total_norm
 
-    def __call__(self, xx, yy, grid):
+    def __call__(self, xx, yy, grid, weight: Optional[float] = None):
+        """``weight``: data parallelism with unequal local batches (fno_b200.data.epoch_plan): the local mean loss is
+        scaled by local_b * world / global_b so that the AVERAGED gradient is the global-batch-mean gradient."""
         loss = nrmse(self.model(xx, grid), yy).mean()
-        self._backward_and_update(loss)
+        self._backward_and_update(loss if weight is None else loss * weight)
         return loss.detach()
 
     def joint(self, xx, yy, grid, xx_aux, yy_aux, grid_aux):
@@ -95,14 +97,16 @@ class FusedTrainStep:
 
     def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-4, t_max: float = 0.0, betas=(0.9, 0.999),
                  eps: float = 1e-8, dp: Optional[BucketedGradAllReduce] = None, graph: bool = False,
-                 auxiliary_weight: Optional[float] = None, alias_inputs: bool = False, max_graphs: int = 2):
+                 auxiliary_weight: Optional[float] = None, alias_inputs: bool = False, max_graphs: int = 2,
+                 param_groups=None):
         from .steptail import FusedClipAdam
 
         self.model = model
         self.dp = dp
         self.aux_w = auxiliary_weight
-        self.opt = FusedClipAdam(model.parameters(), lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
-                                 t_max=t_max, own_grads=dp is None)
+        # param_groups: torch.optim-style group dicts, e.g. the joint loop's three groups (fno_train_aux.py:175-179)
+        self.opt = FusedClipAdam(param_groups if param_groups is not None else model.parameters(), lr=lr, betas=betas,
+                                 eps=eps, weight_decay=weight_decay, t_max=t_max, own_grads=dp is None)
         self.use_graph = graph and dp is None
         self._calls = 0
         self._graph = None
@@ -112,7 +116,7 @@ class FusedTrainStep:
         self.max_graphs = max_graphs
         self._aliased = {}                      # input addresses -> (graph, inputs kept alive, static output)
 
-    def _eager(self, *batch):
+    def _eager(self, *batch, weight=None):
         from .steptail import nrmse_loss
 
         if self.aux_w is None:
@@ -129,15 +133,18 @@ class FusedTrainStep:
             self.dp.zero_grad()
         else:
             self.opt.zero_grad()
-        loss.backward()
+        (loss if weight is None else loss * weight).backward()
         if self.dp is not None:
             self.dp.finish()
         self.opt.step()
         return ret.detach()
 
-    def __call__(self, *batch):
+    def __call__(self, *batch, weight=None):
+        """``weight`` (data parallelism, eager only): see TrainStep.__call__."""
         if not self.use_graph:
-            return self._eager(*batch)
+            return self._eager(*batch, weight=weight)
+        if weight is not None:
+            raise ValueError("FusedTrainStep: a loss weight needs the eager step (graph=False or data parallelism)")
         if self._graph is None:
             if self._calls < 2:                       # eager warm-up: plans, attributes, gradient discovery
                 self._calls += 1

@@ -112,3 +112,69 @@ def test_fno_bucket_names_cover_every_parameter_once():
         assert sorted(flat) == sorted(n for n, _ in model.named_parameters())
         assert len(flat) == len(set(flat))
         assert groups[0][0].startswith("fc1") and any(n.startswith("fc0") for n in groups[4])
+
+
+# ------------------------------------------------------------------------------------------------
+# ragged last global batch (DataLoader(drop_last=False), fno/train.py:95-97): unequal and EMPTY rank slices
+# ------------------------------------------------------------------------------------------------
+def test_epoch_plan_every_rank_every_step():
+    from fno_b200.data import epoch_indices, epoch_plan
+
+    n_items, batch, world = 21, 8, 4                       # global batches 8, 8, 5 -> tail slices 2, 1, 1, 1
+    for n_items in (21, 17, 8):                            # 17: tail of 1 item < world -> three empty slices
+        plans = [epoch_plan(n_items, batch, True, 16, 0, r, world) for r in range(world)]
+        steps = len(plans[0])
+        assert all(len(p) == steps for p in plans) and steps == -(-n_items // batch)
+        for s in range(steps):
+            assert all(p[s][0].numel() >= 1 for p in plans)                     # nobody skips a step
+            gb = min(batch, n_items - s * batch)
+            assert abs(sum(p[s][1] for p in plans) - world) < 1e-12                 # weights average to 1
+            real = [p[s][0] for p in plans if p[s][1] > 0]
+            assert sum(t.numel() for t in real) == gb
+        # union over ranks of the weighted items = the single-process order
+        single = torch.cat(epoch_indices(n_items, batch, True, 16, 0))
+        multi = torch.cat([torch.cat([p[s][0] for p in plans if p[s][1] > 0]) for s in range(steps)])
+        assert sorted(single.tolist()) == sorted(multi.tolist())
+
+
+def _ragged_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fno_b200.data import epoch_plan
+    from fno_b200.dp import BucketedGradAllReduce
+
+    torch.manual_seed(16)
+    model = Tiny()
+    dp = BucketedGradAllReduce(model, [["fc1.weight", "fc1.bias"], ["weights1", "fc0.weight", "fc0.bias", "dead"]])
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    g = torch.Generator().manual_seed(0)
+    X, Y = torch.randn(9, 3, generator=g), torch.randn(9, 2, generator=g)      # 9 items, global batch 4: tail of 1 item
+    for items, w in epoch_plan(9, 4, True, 16, 0, rank, world):
+        loss = ((model(X[items]) - Y[items]) ** 2).mean() * w
+        dp.zero_grad()
+        loss.backward()
+        dp.finish()
+        opt.step()
+    if rank == 0:
+        torch.save(model.state_dict(), os.path.join(out_dir, "ragged.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_ragged_tail_world2_gloo_matches_single_process(tmp_path):
+    from fno_b200.data import epoch_indices
+
+    mp.spawn(_ragged_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = torch.load(tmp_path / "ragged.pt")
+    torch.manual_seed(16)
+    model = Tiny()
+    opt = torch.optim.SGD(model.parameters(), lr=1e-2)
+    g = torch.Generator().manual_seed(0)
+    X, Y = torch.randn(9, 3, generator=g), torch.randn(9, 2, generator=g)
+    for items in epoch_indices(9, 4, True, 16, 0):
+        loss = ((model(X[items]) - Y[items]) ** 2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    for k, v in model.state_dict().items():
+        assert torch.allclose(got[k], v, rtol=1e-5, atol=1e-6), k

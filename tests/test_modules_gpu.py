@@ -116,13 +116,22 @@ def _load_params(model, golden, name):
     return model
 
 
-@pytest.mark.parametrize("name", ["fno2d", "fno3d", "aux2d"])
+@pytest.mark.parametrize("name", ["fno2d", "fno3d", "aux2d", "aux3d"])
 def test_models_vs_reference_golden(golden_models, name):
     from fno_b200 import fno as F
     from fno_b200 import fno_aux as FA
 
     g = golden_models
-    if name == "fno2d":
+    if name == "aux3d":
+        # two-head FNO3d (fno_aux/fno_aux.py:325-475): tests/golden/aux3d_small.npz, oracle/make_golden_aux3d.py
+        import json
+        from pathlib import Path
+        gdir = Path(__file__).resolve().parent / "golden"
+        g = np.load(gdir / "aux3d_small.npz")
+        meta = json.loads((gdir / "aux3d_meta.json").read_text())
+        model = FA.FNO3d(**meta["ctor"])
+        inputs = ("aux3d_x", "aux3d_grid", "aux3d_xa", "aux3d_ga")
+    elif name == "fno2d":
         model = F.FNO2d(num_channels=2, modes1=4, modes2=4, width=8, initial_step=3)
         inputs = ("fno2d_x", "fno2d_grid")
     elif name == "fno3d":
@@ -149,6 +158,9 @@ def test_models_vs_reference_golden(golden_models, name):
             assert O.rel_err(params[k[len(pre):]].grad.cpu().numpy(), g[k]) < 2e-5, k
             n += 1
     assert n >= 6
+    if name == "aux3d":
+        dead = [k for k, q in model.named_parameters() if q.grad is None]
+        assert dead == meta["params_without_grad"]          # the dead BatchNorm3d parameters, as in the reference
 
 
 def test_fno2d_cfg1_vs_reference_samples(golden_cfg1):
@@ -229,3 +241,24 @@ def test_eval_and_train_step_run_without_host_sync_errors():
     loss = P.nrmse(model(x, grid), torch.randn_like(y0)).mean()
     P.train_step_tail(loss, model.parameters(), opt)
     assert (model.conv2.weights1.detach() - before).abs().max().item() > 0
+
+
+def test_compl_mul_is_differentiable_like_the_reference_einsum():
+    """SpectralConv2d_fast.compl_mul2d / SpectralConv3d.compl_mul3d (fno.py:66-68, :255-257) keep their autograd."""
+    from fno_b200.spectral import SpectralConv2d_fast, SpectralConv3d
+
+    g = torch.Generator().manual_seed(4)
+    for mod, shp in ((SpectralConv2d_fast(3, 4, 5, 6), (2, 3, 5, 6)), (SpectralConv3d(2, 3, 3, 4, 3), (2, 2, 3, 4, 3))):
+        mod = mod.cuda()
+        x = torch.randn(shp, generator=g, dtype=torch.cfloat).cuda().requires_grad_(True)
+        w = mod.weights1
+        out = (mod.compl_mul2d if x.dim() == 4 else mod.compl_mul3d)(x, w)
+        gy = torch.randn(out.shape, generator=g, dtype=torch.cfloat).cuda()
+        out.backward(gy)
+        xr = x.detach().clone().requires_grad_(True)
+        wr = w.detach().clone().requires_grad_(True)
+        ref = torch.einsum("bixy,ioxy->boxy" if x.dim() == 4 else "bixyz,ioxyz->boxyz", xr, wr)
+        ref.backward(gy)
+        for a, b in ((out, ref), (x.grad, xr.grad), (w.grad, wr.grad)):
+            assert O.rel_err(torch.view_as_real(a.detach()).cpu().numpy(), torch.view_as_real(b.detach()).cpu().numpy()) < TOL
+        mod.weights1.grad = None
