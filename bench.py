@@ -95,6 +95,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (weak scaling); 0 = the configuration's default")
     ap.add_argument("--config", type=int, default=1, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (see above)")
+    ap.add_argument("--dp-eager", action="store_true",
+                    help="data-parallel runs: eager step with hook-issued, overlapped all-reduces instead of two CUDA "
+                         "graphs around inline bucket all-reduces")
     ap.add_argument("--no-torch-gpu", action="store_true", help="skip the stock-PyTorch-on-the-same-GPU baseline")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-batch", type=int, default=0,
@@ -433,8 +436,8 @@ def run_ours(args):
                   {"params": model.fc2_primary.parameters(), "lr": WL["lr_fc2"]},
                   {"params": model.fc2_auxiliary.parameters(), "lr": WL["lr_fc2"]}]
         step = FusedTrainStep(model, lr=WL["lr_share"], weight_decay=1e-4, t_max=100000, dp=dp,
-                              graph=(args.tail == "graph" and world == 1), alias_inputs=True, max_graphs=4,
-                              auxiliary_weight=WL["aux_w"], param_groups=groups)
+                              graph=(args.tail == "graph" and (world == 1 or not args.dp_eager)), alias_inputs=True,
+                              max_graphs=4, auxiliary_weight=WL["aux_w"], param_groups=groups)
         eager_step = step._eager
     elif args.tail == "torch":
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=1e-4)
@@ -445,9 +448,9 @@ def run_ours(args):
         # the graph reads the input buffers in place (one captured graph per buffer set: the two HBM-resident
         # batches and the two end-to-end staging sets) -- no 201 MB device copy per step
         step = FusedTrainStep(model, lr=1e-3, weight_decay=1e-4, t_max=100000, dp=dp,
-                              graph=(args.tail == "graph" and world == 1), alias_inputs=True, max_graphs=4)
+                              graph=(args.tail == "graph" and (world == 1 or not args.dp_eager)), alias_inputs=True, max_graphs=4)
         eager_step = step._eager
-    graphed = args.tail == "graph" and world == 1
+    graphed = args.tail == "graph" and (world == 1 or not args.dp_eager)
 
     # two distinct host batches per rank (pinned); device copies for the HBM-resident measurement
     host = []
@@ -655,7 +658,7 @@ def run_ours(args):
         "ms_per_step": round(ms_total / K, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": dict(bench_config(args, world, B),
-                       step_tail=args.tail if (world == 1 or args.tail == "torch") else "fused",
+                       step_tail=args.tail if (world == 1 or args.tail == "torch" or graphed) else "fused",
                        l2_policy=f"inputs larger than L2: two alternating {h2d_bytes / 1e6:.0f} MB input batches, activation "
                                  f"tensors of {algorithmic_bytes('pointwise_fwd', B * (1 + WL.get('num_aux', 0))) / 2e6:.0f} MB"),
         "e2e": e2e, "e2e_device_dataset": e2e_dev, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
@@ -707,7 +710,7 @@ def run_sweep(args):
         torch.manual_seed(16)
         model = make_model().to(dev)
         dp = BucketedGradAllReduce(model) if world > 1 else None
-        step = FusedTrainStep(model, lr=1e-3, weight_decay=1e-4, t_max=100000, dp=dp, graph=(world == 1), alias_inputs=True,
+        step = FusedTrainStep(model, lr=1e-3, weight_decay=1e-4, t_max=100000, dp=dp, graph=True, alias_inputs=True,
                               max_graphs=2)
         devb = [tuple(t.to(dev) for t in make_batch(b, 1000 * rank + i)) for i in range(2)]
         for i in range(W):
@@ -722,7 +725,7 @@ def run_sweep(args):
         ms = maxr(e0.elapsed_time(e1))
         barrier()
         points.append({"global_batch": G, "per_gpu_batch": b, "samples_per_s": round(G * K / (ms / 1e3), 1),
-                       "ms_per_step": round(ms / K, 3), "step": "cuda-graph" if world == 1 else "eager fused + bucketed all-reduce"})
+                       "ms_per_step": round(ms / K, 3), "step": "cuda-graph" if world == 1 else "two cuda graphs around the bucket all-reduces"})
         del step, dp, devb
         torch.cuda.empty_cache()
     # rollout evaluation: 5 autoregressive steps on this rank's shard of a 64-item validation set

@@ -92,8 +92,9 @@ class FusedTrainStep:
     per step at batch 128): one graph is captured per distinct set of input addresses (up to
     ``max_graphs``; a double-buffered input pipeline needs two), the caller keeps those tensors alive
     and refills them between steps; other inputs fall back to the copying graph.  Under data
-    parallelism (``dp``) the step stays eager: the bucket all-reduces are issued from autograd
-    hooks and the optimizer reads the reduced bucket views in place (``own_grads=False``)."""
+    parallelism (``dp``) the optimizer reads the reduced bucket views in place (``own_grads=False``); with
+    ``graph=True`` the step is two graph replays around the bucket all-reduces (issued in ``dp.finish()`` on the same
+    stream); without it they are issued from autograd hooks and overlap the rest of the backward pass."""
 
     def __init__(self, model, lr: float = 1e-3, weight_decay: float = 1e-4, t_max: float = 0.0, betas=(0.9, 0.999),
                  eps: float = 1e-8, dp: Optional[BucketedGradAllReduce] = None, graph: bool = False,
@@ -107,7 +108,10 @@ class FusedTrainStep:
         # param_groups: torch.optim-style group dicts, e.g. the joint loop's three groups (fno_train_aux.py:175-179)
         self.opt = FusedClipAdam(param_groups if param_groups is not None else model.parameters(), lr=lr, betas=betas,
                                  eps=eps, weight_decay=weight_decay, t_max=t_max, own_grads=dp is None)
-        self.use_graph = graph and dp is None
+        # data parallelism + graph: two graphs around the (eager, inline) bucket all-reduces -- see _capture
+        self.use_graph = graph
+        if graph and dp is not None:
+            dp.set_inline(True)
         self._calls = 0
         self._graph = None
         self._static_in = None
@@ -116,7 +120,7 @@ class FusedTrainStep:
         self.max_graphs = max_graphs
         self._aliased = {}                      # input addresses -> (graph, inputs kept alive, static output)
 
-    def _eager(self, *batch, weight=None):
+    def _fwd_bwd(self, *batch, weight=None):
         from .steptail import nrmse_loss
 
         if self.aux_w is None:
@@ -134,24 +138,51 @@ class FusedTrainStep:
         else:
             self.opt.zero_grad()
         (loss if weight is None else loss * weight).backward()
+        return ret.detach()
+
+    def _eager(self, *batch, weight=None):
+        ret = self._fwd_bwd(*batch, weight=weight)
         if self.dp is not None:
             self.dp.finish()
         self.opt.step()
-        return ret.detach()
+        return ret
+
+    def _capture(self, batch):
+        """Returns (replay, static output).  Single GPU: forward + loss + backward + update in ONE graph.  Data parallel:
+        TWO graphs around the gradient exchange -- forward + loss + backward, then (eagerly, on the same stream) one NCCL
+        all-reduce per bucket, then the optimizer graph.  (Capturing the collectives themselves was tried on 2 B200s in
+        rounds 1 and 2 and hung during capture; with 2 graph launches + 5 NCCL calls the step no longer pays for ~150
+        kernel launches.)"""
+        if self.dp is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self._eager(*batch)
+            return g.replay, out
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            out = self._fwd_bwd(*batch)
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self.opt.step()
+
+        def replay():
+            g1.replay()
+            self.dp.finish()
+            g2.replay()
+        return replay, out
 
     def __call__(self, *batch, weight=None):
         """``weight`` (data parallelism, eager only): see TrainStep.__call__."""
         if not self.use_graph:
             return self._eager(*batch, weight=weight)
         if weight is not None:
-            raise ValueError("FusedTrainStep: a loss weight needs the eager step (graph=False or data parallelism)")
+            raise ValueError("FusedTrainStep: a loss weight needs the eager step (graph=False)")
         if self._graph is None:
             if self._calls < 2:                       # eager warm-up: plans, attributes, gradient discovery
                 self._calls += 1
                 return self._eager(*batch)
             # third call: this batch's step runs eagerly on a side stream (the stream-capture warm-up
             # PyTorch asks for), then the same sequence is captured -- capture records, it does not
-            # execute -- and every later call is one graph replay
+            # execute -- and every later call is a graph replay
             self._static_in = tuple(torch.empty_like(t) for t in batch)
             for dst, src in zip(self._static_in, batch):
                 dst.copy_(src)
@@ -160,9 +191,7 @@ class FusedTrainStep:
             with torch.cuda.stream(side):
                 ret = self._eager(*self._static_in)
             torch.cuda.current_stream().wait_stream(side)
-            self._graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph):
-                self._static_out = self._eager(*self._static_in)
+            self._graph, self._static_out = self._capture(self._static_in)
             return ret
         elif self.alias_inputs and all(t.is_contiguous() for t in batch):
             key = tuple((t.data_ptr(), tuple(t.shape)) for t in batch)
@@ -170,17 +199,15 @@ class FusedTrainStep:
             if hit is None and len(self._aliased) < self.max_graphs:
                 # same parameters, optimizer state and step counter; only the input addresses differ.  Capture
                 # records, it does not execute: the replay below runs this batch's step.
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    out = self._eager(*batch)
-                hit = self._aliased[key] = (g, batch, out)
+                replay, out = self._capture(batch)
+                hit = self._aliased[key] = (replay, batch, out)
             if hit is not None:
-                hit[0].replay()
+                hit[0]()
                 return hit[2]
             for dst, src in zip(self._static_in, batch):
                 dst.copy_(src, non_blocking=True)
         else:
             for dst, src in zip(self._static_in, batch):
                 dst.copy_(src, non_blocking=True)
-        self._graph.replay()
+        self._graph()
         return self._static_out
