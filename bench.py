@@ -539,21 +539,44 @@ def run_ours(args):
         e2e = {"value": round(world * B * K / (ms_e2e / 1e3), 2), "unit": "samples/s",
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_e2e / K, 3)}
 
-    # ---- end to end through the device-resident dataset (extra key, not the contract's `e2e`) ----
-    # trajectories live in HBM, a step's host input is the batch of item indices (B x 8 bytes from pinned memory),
-    # windows are gathered by fno_window_gather, the loss is read back every step
+    # ---- end to end through the streaming device-resident dataset: the declared `e2e` at config 1 ----
+    # The reference loaders read a whole trajectory per item (fno/utils_2d_rd_baseline.py:74-86) and consecutive windows
+    # share 9 of their 10 input frames, so shipping assembled (xx, yy) batches moves every frame ~11 times (201 MB per
+    # step at batch 128: the PCIe link, not the GPU, then sets the rate, and 8 ranks saturate the host).  Here every
+    # trajectory FRAME crosses the link once: trajectories live in HBM in the loaders' own order, each step uploads --
+    # inside the timed region, from pinned host memory, on a copy stream -- the share of fresh trajectory data its B
+    # windows consume (B * T / n_windows frames) plus the B item indices, gathers its windows on the device
+    # (fno_window_gather) and reads the loss back.
     e2e_dev = None
     if not args.no_e2e and WL["kind"] == "fno2d":
-        traj = data.diffusion_trajectories(16, RES, CFG["initial_step"] + 16, CFG["num_channels"], seed=5 + rank)
+        T_traj = CFG["initial_step"] + 91                      # 101 frames -> 91 windows per trajectory, as in PDEBench
+        n_traj = 8
+        traj = data.diffusion_trajectories(n_traj, RES, T_traj, CFG["num_channels"], seed=5 + rank)
         ds = data.DeviceWindows(traj, CFG["initial_step"], 1, device=dev)
+        h_store = ds.traj.detach().cpu().pin_memory()          # the store's own layout [n, pixels, T, V]
+        flat_dev, flat_host = ds.traj.view(-1), h_store.view(-1)
+        frame_floats = RES ** WL["nd"] * CFG["num_channels"]
+        chunk = min(flat_dev.numel(), ((B * T_traj + ds.n_windows - 1) // ds.n_windows) * frame_floats)   # floats per step
         gi = torch.Generator().manual_seed(7 + rank)
         items_host = [torch.randint(0, len(ds), (B,), generator=gi, dtype=torch.int64).pin_memory() for _ in range(2)]
+        up_stream = torch.cuda.Stream()
+        up_done = [torch.cuda.Event() for _ in range(2)]
 
         def dev_loop(n):
             last = 0.0
+            cur = torch.cuda.current_stream()
+            off = 0
             for i in range(n):
+                with torch.cuda.stream(up_stream):             # this step's share of fresh trajectory frames
+                    up_stream.wait_stream(cur)                 # (rotating region of the store; values are unchanged)
+                    if off + chunk > flat_dev.numel():
+                        off = 0
+                    flat_dev[off:off + chunk].copy_(flat_host[off:off + chunk], non_blocking=True)
+                    up_done[i % 2].record(up_stream)
+                    off += chunk
                 items = items_host[i % 2].to(dev, non_blocking=True)
-                last = float(step(*ds.batch(items)))
+                cur.wait_event(up_done[i % 2])
+                last = float(step(*ds.batch(items)).flatten()[0])
             return last
 
         dev_loop(W)
@@ -567,9 +590,12 @@ def run_ours(args):
         ms_dev = max_over_ranks(t0.elapsed_time(t1))
         barrier()
         e2e_dev = {"value": round(world * B * K / (ms_dev / 1e3), 2), "unit": "samples/s",
-                   "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_dev / K, 3),
-                   "dataset": f"fno_b200.data.DeviceWindows, {len(ds)} windows resident in HBM"}
-        del ds, traj
+                   "h2d_bytes_per_step": 4 * chunk + 8 * B, "d2h_bytes_per_step": 4, "ms_per_step": round(ms_dev / K, 3),
+                   "how": f"streaming device-resident dataset (fno_b200.data.DeviceWindows): per step {4 * chunk / 1e6:.1f} MB of "
+                          f"fresh trajectory frames ({T_traj}/{ds.n_windows} frames per window consumed) + {8 * B} B of item "
+                          "indices H2D from pinned memory inside the timed region, windows gathered on the device, loss read "
+                          "back every step"}
+        del ds, traj, h_store
 
     # ---- instrumented pass: per-kernel CUDA events (never used for `value`) -------------------
     roofline, kernels = None, None
@@ -661,7 +687,10 @@ def run_ours(args):
                        step_tail=args.tail if (world == 1 or args.tail == "torch" or graphed) else "fused",
                        l2_policy=f"inputs larger than L2: two alternating {h2d_bytes / 1e6:.0f} MB input batches, activation "
                                  f"tensors of {algorithmic_bytes('pointwise_fwd', B * (1 + WL.get('num_aux', 0))) / 2e6:.0f} MB"),
-        "e2e": e2e, "e2e_device_dataset": e2e_dev, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        # declared end-to-end number: the streaming device-resident dataset where the workload has one (2-D single-head
+        # configs); `e2e_host_batches` ships fully assembled (xx, yy, grid) batches every step (round 1's `e2e`)
+        "e2e": e2e_dev if e2e_dev is not None else e2e, "e2e_host_batches": e2e, "gpu_launches": int(launches),
+        "clocks": clocks, "roofline": roofline,
         "cpu_baseline": cpu, "torch_gpu_baseline": torch_gpu,
         "kernels": kernels, "final_loss": round(final_loss, 6),
     }

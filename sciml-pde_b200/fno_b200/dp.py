@@ -39,12 +39,17 @@ def _real_view(t: torch.Tensor) -> torch.Tensor:
 
 
 class _Bucket:
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
+    @staticmethod
+    def floats(params) -> int:
+        return sum((_real_view(p).numel() + 3) & ~3 for p in params)
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], storage: Optional[torch.Tensor] = None):
         self.params = list(params)
         dev = self.params[0].device
         sizes = [_real_view(p).numel() for p in self.params]
         padded = [(n + 3) & ~3 for n in sizes]          # 16-byte aligned slots (complex views need even offsets)
-        self.flat = torch.zeros(sum(padded), dtype=torch.float32, device=dev)
+        # `storage`: a slice of one buffer shared by all buckets, so that the inline mode can exchange everything in ONE call
+        self.flat = storage if storage is not None else torch.zeros(sum(padded), dtype=torch.float32, device=dev)
         off = 0
         for p, n, npad in zip(self.params, sizes, padded):
             chunk = self.flat[off:off + n]
@@ -110,10 +115,10 @@ class BucketedGradAllReduce:
             self._discover_and_reduce()
             return
         if self.inline:
-            for b in self.buckets:
-                dist.all_reduce(b.flat, op=self._op, group=self.group)
-                if self._scale_after:
-                    b.flat.mul_(1.0 / self.world)
+            # one collective over the buffer all buckets live in (3.7 MB at cfg 1): latency, not bandwidth, is the cost
+            dist.all_reduce(self._all, op=self._op, group=self.group)
+            if self._scale_after:
+                self._all.mul_(1.0 / self.world)
             return
         for b in self.buckets:
             if b.work is None:          # a parameter of the bucket did not fire this step
@@ -126,8 +131,15 @@ class BucketedGradAllReduce:
     # -- internals ------------------------------------------------------------------------------
     def _discover_and_reduce(self):
         live = {n: p for n, p in self.named.items() if p.grad is not None}
-        groups = [[live[n] for n in names if n in live] for names in self.bucket_names]
-        self.buckets = [_Bucket(g) for g in groups if g]
+        groups = [g for g in ([live[n] for n in names if n in live] for names in self.bucket_names) if g]
+        dev = groups[0][0].device
+        self._all = torch.zeros(sum(_Bucket.floats(g) for g in groups), dtype=torch.float32, device=dev)
+        off = 0
+        self.buckets = []
+        for g in groups:
+            n = _Bucket.floats(g)
+            self.buckets.append(_Bucket(g, self._all[off:off + n]))
+            off += n
         for bi, b in enumerate(self.buckets):
             for p in b.params:
                 self._bucket_of[p] = bi
