@@ -558,25 +558,45 @@ def run_ours(args):
         frame_floats = RES ** WL["nd"] * CFG["num_channels"]
         chunk = min(flat_dev.numel(), ((B * T_traj + ds.n_windows - 1) // ds.n_windows) * frame_floats)   # floats per step
         gi = torch.Generator().manual_seed(7 + rank)
-        items_host = [torch.randint(0, len(ds), (B,), generator=gi, dtype=torch.int64).pin_memory() for _ in range(2)]
+        items_host = [ds.split_items(torch.randint(0, len(ds), (B,), generator=gi, dtype=torch.int64)) for _ in range(2)]
+        npx = RES ** WL["nd"]
+        outs = [(torch.empty(B, npx, CFG["initial_step"], CFG["num_channels"], device=dev),
+                 torch.empty(B, npx, 1, CFG["num_channels"], device=dev)) for _ in range(2)]   # fixed addresses: aliased graphs
         up_stream = torch.cuda.Stream()
         up_done = [torch.cuda.Event() for _ in range(2)]
+        state = {"off": 0}
+
+        def upload(i):                                         # step i's share of fresh trajectory frames (rotating region
+            with torch.cuda.stream(up_stream):                 # of the store, values unchanged), one step ahead of its use
+                if state["off"] + chunk > flat_dev.numel():
+                    state["off"] = 0
+                o = state["off"]
+                flat_dev[o:o + chunk].copy_(flat_host[o:o + chunk], non_blocking=True)
+                up_done[i % 2].record(up_stream)
+                state["off"] = o + chunk
+
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        loss_ev = [torch.cuda.Event() for _ in range(2)]
 
         def dev_loop(n):
+            # host-side software pipeline: the next batch is gathered (queued behind the running step) BEFORE the host
+            # blocks on this step's loss, so the GPU never waits for the host between steps; the loss of every step is
+            # still copied to pinned host memory and read
             last = 0.0
             cur = torch.cuda.current_stream()
-            off = 0
+            upload(0)
+            cur.wait_event(up_done[0])
+            nxt = ds.batch(items_host[0], out=outs[0])
             for i in range(n):
-                with torch.cuda.stream(up_stream):             # this step's share of fresh trajectory frames
-                    up_stream.wait_stream(cur)                 # (rotating region of the store; values are unchanged)
-                    if off + chunk > flat_dev.numel():
-                        off = 0
-                    flat_dev[off:off + chunk].copy_(flat_host[off:off + chunk], non_blocking=True)
-                    up_done[i % 2].record(up_stream)
-                    off += chunk
-                items = items_host[i % 2].to(dev, non_blocking=True)
-                cur.wait_event(up_done[i % 2])
-                last = float(step(*ds.batch(items)).flatten()[0])
+                loss_i = step(*nxt)
+                loss_host[i % 2:i % 2 + 1].copy_(loss_i.flatten()[:1], non_blocking=True)
+                loss_ev[i % 2].record(cur)
+                if i + 1 < n:
+                    upload(i + 1)
+                    cur.wait_event(up_done[(i + 1) % 2])
+                    nxt = ds.batch(items_host[(i + 1) % 2], out=outs[(i + 1) % 2])
+                loss_ev[i % 2].synchronize()
+                last = float(loss_host[i % 2])                 # D2H read of the step's loss (4 bytes)
             return last
 
         dev_loop(W)

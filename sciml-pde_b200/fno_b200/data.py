@@ -165,18 +165,32 @@ class DeviceWindows:
     def __len__(self):
         return self.traj.shape[0] * self.n_windows
 
-    def batch(self, items: torch.Tensor):
-        """items: 1-D int64 (host or device) -> (xx [B,*sp,T0,V], yy [B,*sp,R,V], grid [B,*sp,nd]) on the device."""
-        from . import lib
-
-        items = items.to(device=self.device, dtype=torch.int64)
+    def split_items(self, items: torch.Tensor):
+        """Host-side index arithmetic of a batch: item -> (trajectory index int64, window start int32), pinned."""
+        items = items.to(dtype=torch.int64, device="cpu")
         ti = torch.div(items, self.n_windows, rounding_mode="floor")
         ts = (items - ti * self.n_windows).to(torch.int32)
-        xx, yy = lib.window_gather(self.traj, ti.contiguous(), ts.contiguous(), self.initial_step, self.rollout)
-        B = items.numel()
+        return ti.contiguous().pin_memory(), ts.contiguous().pin_memory()
+
+    def batch(self, items, out=None):
+        """items: 1-D int64 (host or device), or the (ti, ts) pair of ``split_items`` -> (xx [B,*sp,T0,V], yy [B,*sp,R,V],
+        grid [B,*sp,nd]) on the device.  ``out = (xx, yy)``: gather into caller-owned buffers (fixed addresses)."""
+        from . import lib
+
+        if isinstance(items, tuple):
+            ti, ts = (t.to(self.device, non_blocking=True) for t in items)
+            B = ti.numel()
+        else:
+            items = items.to(device=self.device, dtype=torch.int64)
+            ti = torch.div(items, self.n_windows, rounding_mode="floor").contiguous()
+            ts = (items - ti * self.n_windows).to(torch.int32).contiguous()
+            B = items.numel()
+        xx, yy = lib.window_gather(self.traj, ti, ts, self.initial_step, self.rollout, out=out)
         xx = xx.view((B,) + self.spatial + (self.initial_step, self.V))
         yy = yy.view((B,) + self.spatial + (self.rollout, self.V))
-        return xx, yy, self.grid.unsqueeze(0).expand(B, *([-1] * (self.nd + 1)))
+        if getattr(self, "_grid_b", None) is None or self._grid_b.shape[0] != B:
+            self._grid_b = self.grid.unsqueeze(0).expand(B, *([-1] * (self.nd + 1))).contiguous()   # same tensor every step
+        return xx, yy, self._grid_b
 
     def epoch(self, batch: int, shuffle: bool = True, seed: int = 16, epoch: int = 0, rank: int = 0, world: int = 1,
               with_weight: bool = False):

@@ -585,7 +585,8 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
 
 
 @_on_tensor_device
-def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Tensor, initial_step: int, rollout: int):
+def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Tensor, initial_step: int, rollout: int,
+                  out=None):
     """traj [n_traj, pixels, T, V] (device, time-inner) -> xx [B, pixels, initial_step, V], yy [B, pixels, rollout, V]
     for the items (traj_idx[b], t_start[b]); one copy kernel, nothing touches the host."""
     _require(traj, torch.float32, "traj")
@@ -594,8 +595,15 @@ def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Ten
         raise FnoError("window_gather: traj [n, pixels, T, V] f32, traj_idx int64 [B], t_start int32 [B], one device")
     n, npix, T, V = traj.shape
     B = traj_idx.numel()
-    xx = torch.empty((B, npix, initial_step, V), dtype=torch.float32, device=traj.device)
-    yy = torch.empty((B, npix, rollout, V), dtype=torch.float32, device=traj.device)
+    if out is not None:                      # caller-owned (xx, yy): fixed addresses for CUDA-graph steps that alias them
+        xx, yy = out
+        _require(xx, torch.float32, "xx")
+        _require(yy, torch.float32, "yy")
+        if xx.numel() != B * npix * initial_step * V or yy.numel() != B * npix * rollout * V:
+            raise FnoError("window_gather: out buffers have the wrong size")
+    else:
+        xx = torch.empty((B, npix, initial_step, V), dtype=torch.float32, device=traj.device)
+        yy = torch.empty((B, npix, rollout, V), dtype=torch.float32, device=traj.device)
     _check(load().fno_window_gather(traj.data_ptr(), traj_idx.data_ptr(), t_start.data_ptr(), xx.data_ptr(),
                                     yy.data_ptr(), B, npix, T, V, initial_step, rollout, _stream()),
            "fno_window_gather")
