@@ -77,92 +77,14 @@ __device__ __forceinline__ void tmem_st4(unsigned taddr, const float (&v)[4]) {
                : "memory");
 }
 
-// ------------------------------------------------------------------------------------------------------
-// spectral part of the edge columns w = Wm + j (j < RE) that do not fit the 128 TMEM lanes:
-//   E[plane, h, j] = Re sum_{r, q} sc_q Y[r, q] e^{+2 pi i (k_r h / H + q w_j / W)}
-// contiguous axis first (U[r, j] = sum_q sc_q Y[r, q] e^{i phi_q w_j}, 2 m1 x RE complex numbers per plane, shared
-// memory), then the strided axis per row.  0.1 % of the layer's flops; the main kernel's edge warp adds the bypass.
-// ------------------------------------------------------------------------------------------------------
-constexpr int HE_PB = 4;      // planes per block
+// arguments for the spectral part of the edge columns w = Wm + j that do not fit the 128 TMEM lanes (W > 128):
+//   E[plane, h, j] = Re sum_{r, q} sc_q Y[r, q] e^{+2 pi i (k_r h / H + q w_j / W)} = sum_q' F[w_j, q'] T2[h, q']
 struct EdgeArgs {
   float* E;             // [planes][H][RE]
   const float* twW;
   int WP, Wm, RE, r_edge, shift;
 };
 
-template <int M1T>
-__device__ __forceinline__ void hinv_edge_block(const float2* __restrict__ Y, const EdgeArgs& ea, const float* __restrict__ twH,
-                                                int H, int W, int m1, int m2, long p0, long planes, int cmode, float scale) {
-  constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
-  __shared__ float2 U[HE_PB][2 * M1T][L2_RMAX];
-  __shared__ float2 PM[HE_PB][M1T + 1][L2_RMAX];      // (Re(U[+j] + U[-j]), Im(U[+j] - U[-j])): all the real part needs
-  float* __restrict__ E = ea.E;
-  const float* __restrict__ twW = ea.twW;
-  const int WP = ea.WP, Wm = ea.Wm, RE = ea.RE, r_edge = ea.r_edge, shift = ea.shift;
-  const int R = 2 * m1;
-  // column slot u: u < r_edge -> w = Wm + u (rows whose window is [0, Wm)); with `shift`, r_edge <= u < 2 r_edge ->
-  // w = u - r_edge (rows whose tensor-map window is [r_edge, Wm + r_edge))
-  const int ncol = shift ? 2 * r_edge : r_edge;
-  for (int i = threadIdx.x; i < HE_PB * R * L2_RMAX; i += blockDim.x) {
-    const int u = i % L2_RMAX, r = (i / L2_RMAX) % R, pl = i / (L2_RMAX * R);
-    float2 acc = make_float2(0.f, 0.f);
-    if (p0 + pl < planes && u < ncol) {
-      const int wcol = u < r_edge ? Wm + u : u - r_edge;
-      const float2* __restrict__ yp = Y + ((size_t)(p0 + pl) * R + r) * m2;
-#pragma unroll 4
-      for (int q = 0; q < m2; ++q) {
-        float sc = scale;
-        if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
-        const float2 y = __ldg(yp + q);
-        const float c = sc * __ldg(twW + (size_t)q * WP + wcol), sn = sc * __ldg(twW + (size_t)(m2 + q) * WP + wcol);
-        acc.x = fmaf(y.x, c, acc.x); acc.x = fmaf(-y.y, sn, acc.x);
-        acc.y = fmaf(y.x, sn, acc.y); acc.y = fmaf(y.y, c, acc.y);
-      }
-    }
-    U[pl][r][u] = acc;
-  }
-  __syncthreads();
-  // fold the signed frequencies: Re sum_k U[k] e^{i k x} = U[0].x + sum_j (Re(U[j] + U[-j]) cos(j x) - Im(U[j] - U[-j]) sin(j x))
-  for (int i = threadIdx.x; i < HE_PB * (m1 + 1) * L2_RMAX; i += blockDim.x) {
-    const int u = i % L2_RMAX, jj = (i / L2_RMAX) % (m1 + 1), pl = i / (L2_RMAX * (m1 + 1));
-    float2 v;
-    if (jj == 0) {
-      v = make_float2(U[pl][0][u].x, 0.f);
-    } else {
-      const float2 up = (jj < m1) ? U[pl][jj][u] : make_float2(0.f, 0.f);
-      const float2 un = U[pl][R - jj][u];
-      v = make_float2(up.x + un.x, up.y - un.y);
-    }
-    PM[pl][jj][u] = v;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < HE_PB * H; i += blockDim.x) {
-    const int h = i % H, pl = i / H;
-    if (p0 + pl >= planes) break;
-    const int t = (2 * h <= H) ? h : H - h;
-    const float sg = (2 * h <= H) ? 1.0f : -1.0f;
-    const float* __restrict__ tw = twH + (size_t)t * JP;
-    const int u0 = (shift && (((unsigned)h * (unsigned)W) & 3u)) ? r_edge : 0;       // this row's column slots
-    float e0 = PM[pl][0][u0].x, e1 = (u0 + 1 < L2_RMAX) ? PM[pl][0][u0 + 1].x : 0.f;
-    float e2 = 0.f, e3 = 0.f;
-    if (RE > 2) { e2 = PM[pl][0][2].x; e3 = PM[pl][0][3].x; }
-    for (int jj = 1; jj <= m1; ++jj) {
-      const float c = __ldg(tw + jj), sn = sg * __ldg(tw + M1T + jj);
-      const float2 a0 = PM[pl][jj][u0], a1 = PM[pl][jj][(u0 + 1) & (L2_RMAX - 1)];
-      e0 = fmaf(a0.x, c, e0); e0 = fmaf(-a0.y, sn, e0);
-      e1 = fmaf(a1.x, c, e1); e1 = fmaf(-a1.y, sn, e1);
-      if (RE > 2) {
-        const float2 a2 = PM[pl][jj][2], a3 = PM[pl][jj][3];
-        e2 = fmaf(a2.x, c, e2); e2 = fmaf(-a2.y, sn, e2);
-        e3 = fmaf(a3.x, c, e3); e3 = fmaf(-a3.y, sn, e3);
-      }
-    }
-    float* __restrict__ o = E + ((size_t)(p0 + pl) * H + h) * RE;
-    o[0] = e0;
-    o[1] = e1;
-    if (RE > 2) { o[2] = e2; o[3] = e3; }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------------
 // strided-axis inverse into B-operand tiles:  Z[h, q] = sum_r Y[r, q] e^{+2 pi i k_r h / H}  (k_r signed),
@@ -177,26 +99,11 @@ __global__ void __launch_bounds__(256)
 hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const float* __restrict__ twH, int H, int W,
                   int m1, int m2, int C, int D1, int KQ, int tile_floats, int TL, int cmode, float scale, const EdgeArgs ea) {
   constexpr int JP = ((2 * M1T + 1) + 3) & ~3;
-  if (blockIdx.z == (C + 7) / 8) {
-    // extra blocks of the same launch: the spectral part of the edge columns for a slice of this sample's channels
-    const int cpb = (C + (int)gridDim.y - 1) / (int)gridDim.y;          // channels per block
-    const int c_lo = blockIdx.y * cpb, c_hi = (c_lo + cpb < C) ? c_lo + cpb : C;
-    const long bd = blockIdx.x;                                        // b * D1 + d1
-    const long b = bd / D1, d1 = bd - b * D1;
-    for (int c0 = c_lo; c0 < c_hi; c0 += HE_PB) {
-      // planes (b * C + c) * D1 + d1 are D1 apart: handle one at a time when D1 > 1
-      if (D1 == 1) {
-        hinv_edge_block<M1T>(Y, ea, twH, H, W, m1, m2, b * C + c0, b * C + c_hi, cmode, scale);
-      } else {
-        for (int c = c0; c < c_hi && c < c0 + HE_PB; ++c)
-          hinv_edge_block<M1T>(Y, ea, twH, H, W, m1, m2, (b * C + c) * D1 + d1, (b * C + c) * D1 + d1 + 1, cmode, scale);
-      }
-      __syncthreads();
-    }
-    return;
-  }
   // one block = (sample, slice of row pairs, 8-channel row group): its part of every operand tile is a contiguous
-  // KQ * 32-byte segment, assembled in shared memory (zero padding included) and written out with 16-byte stores
+  // KQ * 32-byte segment, assembled in shared memory (zero padding included) and written out with 16-byte stores.
+  // The spectral part of the edge columns (E[plane, h, j] = sum_q' F[w_j, q'] T2[h, q'], W > 128) falls out of the same
+  // values: every thread leaves its two terms in shared memory and the write-out phase sums them over q (shared-memory
+  // atomics were tried: 12-way contention made the kernel 3x slower).
   extern __shared__ float4 hs4[];
   float* hs = reinterpret_cast<float*>(hs4);
   const int q = threadIdx.x % m2, cl = threadIdx.x / m2;
@@ -206,6 +113,8 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
   const int NP = H / 2 + 1;
   const int t0 = blockIdx.y * TL, t1 = (t0 + TL < NP) ? t0 + TL : NP;
   const int seg = KQ * 8;                     // floats of one (row, row group) segment
+  const int RE = ea.RE, r_edge = ea.r_edge;
+  float* es = hs + 2 * TL * seg;              // [2 TL rows][8 channels][RE][m2] partial edge sums
   for (int i = threadIdx.x; i < 2 * TL * seg / 4; i += blockDim.x) hs4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   if (active) {
@@ -224,9 +133,25 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
     }
     float sc = scale;
     if (cmode && q != 0 && !((W & 1) == 0 && 2 * q == W)) sc *= 2.0f;
+    // twiddles of this thread's wavenumber at the edge columns: slot u < r_edge -> w = Wm + u; with `shift`,
+    // r_edge <= u < 2 r_edge -> w = u - r_edge (rows whose tensor-map window is [r_edge, Wm + r_edge))
+    float fc[L2_RMAX], fs[L2_RMAX];
+#pragma unroll
+    for (int u = 0; u < L2_RMAX; ++u) {
+      const int ncol = ea.shift ? 2 * r_edge : r_edge;
+      const int wcol = u < r_edge ? ea.Wm + u : u - r_edge;
+      fc[u] = (u < ncol) ? __ldg(ea.twW + (size_t)q * ea.WP + wcol) : 0.f;
+      fs[u] = (u < ncol) ? __ldg(ea.twW + (size_t)(m2 + q) * ea.WP + wcol) : 0.f;
+    }
     const int o_re = (q >> 2) * 32 + cl * 4 + (q & 3), o_im = ((m2 + q) >> 2) * 32 + cl * 4 + ((m2 + q) & 3);
-    for (int t = t0; t < t1; ++t) {
-      const float4* __restrict__ r4 = reinterpret_cast<const float4*>(twH + (size_t)t * JP);
+    // all addresses advance by constants per row pair (integer index arithmetic was half of this kernel's instructions)
+    float* __restrict__ o = hs;                                  // row t, then its mirror H - t: 2 seg floats per pair
+    float* __restrict__ e = es + (size_t)cl * RE * m2 + q;       // [slot][ch][j][q]; the mirror row is 8 RE m2 further
+    const int mo = 8 * RE * m2;
+    const float4* __restrict__ r4 = reinterpret_cast<const float4*>(twH + (size_t)t0 * JP);
+    // with `shift` (W % 4 == 2) a row's column window -- hence its edge column pair -- depends on the parity of the row
+    const bool hodd = (H & 1) != 0;
+    for (int t = t0; t < t1; ++t, o += 2 * seg, e += 2 * mo, r4 += JP / 4) {
       float tw[JP];
 #pragma unroll
       for (int i = 0; i < JP / 4; ++i) {
@@ -241,22 +166,61 @@ hinv_tiles_kernel(const float2* __restrict__ Y, float* __restrict__ T2g, const f
         odr = fmaf(MI[j], tw[M1T + j], odr);
         odi = fmaf(MR[j], tw[M1T + j], odi);
       }
-      float* __restrict__ o = hs + (size_t)(2 * (t - t0)) * seg;       // row t, then its mirror H - t
-      o[o_re] = sc * (er - odr);
-      o[o_im] = -sc * (ei + odi);
-      o[seg + o_re] = sc * (er + odr);
-      o[seg + o_im] = -sc * (ei - odi);
+      const float a_re = sc * (er - odr), a_im = -sc * (ei + odi);
+      const float b_re = sc * (er + odr), b_im = -sc * (ei - odi);
+      o[o_re] = a_re;
+      o[o_im] = a_im;
+      o[seg + o_re] = b_re;
+      o[seg + o_im] = b_im;
+      if (r_edge > 0) {
+        if (ea.shift) {                                        // r_edge <= 2
+          const bool sa = (t & 1) != 0, sb = sa != hodd;       // parity of rows t and H - t
+          e[0] = fmaf(sa ? fc[2] : fc[0], a_re, (sa ? fs[2] : fs[0]) * a_im);
+          e[mo] = fmaf(sb ? fc[2] : fc[0], b_re, (sb ? fs[2] : fs[0]) * b_im);
+          if (RE > 1) {
+            e[m2] = fmaf(sa ? fc[3] : fc[1], a_re, (sa ? fs[3] : fs[1]) * a_im);
+            e[mo + m2] = fmaf(sb ? fc[3] : fc[1], b_re, (sb ? fs[3] : fs[1]) * b_im);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < L2_RMAX; ++j) {
+            if (j < RE) {
+              e[j * m2] = fmaf(fc[j], a_re, fs[j] * a_im);
+              e[mo + j * m2] = fmaf(fc[j], b_re, fs[j] * b_im);
+            }
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  float* __restrict__ base = T2g + (size_t)bd * H * tile_floats + (size_t)blockIdx.z * seg;
+  // write-out: thread f copies float4 f of every segment (running pointers: rows t ascend, their mirrors descend)
   const int seg4 = seg / 4;
-  for (int i = threadIdx.x; i < 2 * (t1 - t0) * seg4; i += blockDim.x) {
-    const int slot = i / seg4, f = i - slot * seg4;
-    const int t = t0 + (slot >> 1);
-    if ((slot & 1) && (t == 0 || 2 * t == H)) continue;               // self-paired rows have no mirror
-    const int row = (slot & 1) ? H - t : t;
-    reinterpret_cast<float4*>(base + (size_t)row * tile_floats)[f] = hs4[i];
+  if ((int)threadIdx.x < seg4) {
+    float* __restrict__ base = T2g + (size_t)bd * H * tile_floats + (size_t)blockIdx.z * seg;
+    float4* __restrict__ da = reinterpret_cast<float4*>(base + (size_t)t0 * tile_floats) + threadIdx.x;
+    float4* __restrict__ db = reinterpret_cast<float4*>(base + (size_t)(H - t0) * tile_floats) + threadIdx.x;
+    const float4* __restrict__ src = hs4 + threadIdx.x;
+    const int tf4 = tile_floats / 4;
+    for (int t = t0; t < t1; ++t, da += tf4, db -= tf4, src += 2 * seg4) {
+      *da = src[0];
+      if (t != 0 && 2 * t != H) *db = src[seg4];               // self-paired rows have no mirror
+    }
+  }
+  if (r_edge > 0) {
+    // RE is 2 or 4: item i = (slot, channel, j)
+    const int lre = RE == 4 ? 2 : 1;
+    const int b = bd / D1, d1 = bd - b * D1;
+    for (int i = threadIdx.x; i < 2 * (t1 - t0) * 8 * RE; i += blockDim.x) {
+      const int j = i & (RE - 1), ch = (i >> lre) & 7, slot = i >> (lre + 3);
+      const int t = t0 + (slot >> 1), cc = blockIdx.z * 8 + ch;
+      if (cc >= C || ((slot & 1) && (t == 0 || 2 * t == H))) continue;
+      const int row = (slot & 1) ? H - t : t;
+      const float* __restrict__ pq = es + (size_t)i * m2;
+      float sum = 0.f;
+      for (int qq = 0; qq < m2; ++qq) sum += pq[qq];
+      ea.E[((((size_t)b * C + cc) * D1 + d1) * H + row) * RE + j] = sum;
+    }
   }
 }
 
@@ -898,13 +862,13 @@ int launch_hinv_t(const Plan* p, const float* Y, float* T2g, int B, int C, int K
   // row-pair slices: enough CTAs for ~4 waves of small blocks
   const long base = (long)B * p->D1 * ((C + 7) / 8);
   int TS = (int)((4L * 148 * 4 + base - 1) / base);
+  { static const int ov = [] { const char* e = std::getenv("FNO_HINV_TS"); return e ? std::atoi(e) : 0; }(); if (ov > 0) TS = ov; }
   if (TS < 1) TS = 1;
   if (TS > NP) TS = NP;
   const int TL = (NP + TS - 1) / TS;
   TS = (NP + TL - 1) / TL;
-  // one more z-slice of blocks computes the spectral part of the edge columns (W > 128) in the same launch
-  dim3 grid((unsigned)(B * p->D1), (unsigned)TS, (unsigned)((C + 7) / 8 + (ea.r_edge > 0 ? 1 : 0)));
-  const size_t smem = sizeof(float) * 2ul * TL * KQ * 8;
+  dim3 grid((unsigned)(B * p->D1), (unsigned)TS, (unsigned)((C + 7) / 8));
+  const size_t smem = sizeof(float) * (2ul * TL * KQ * 8 + 2ul * TL * 8 * ea.RE * p->m2);
   if (smem > 48 * 1024) { set_error("hinv_tiles: row slice too large"); return FNO_E_ARG; }
   hinv_tiles_kernel<M1T><<<grid, threads, smem, st>>>(reinterpret_cast<const float2*>(Y), T2g, p->twH, p->H, p->W, p->m1, p->m2,
                                                   C, p->D1, KQ, tile_floats, TL, cmode, scale, ea);
