@@ -115,7 +115,6 @@ int build_tc_tables(Plan* p) {
   const int KP = (W + 7) & ~7;
   const int nch = KP / 4;
   if ((W & 1) || 2 * m2 > 32 || nch > 34) return FNO_OK;   // not eligible: FP32 path only
-  if (fwd2d_tc_smem_bytes(nch) > 227 * 1024) return FNO_OK;
   std::vector<float> hi((size_t)4 * nch * 32, 0.0f), lo((size_t)4 * nch * 32, 0.0f);
   for (int q = 0; q < 2 * m2; ++q)
     for (int w = 0; w < W; ++w) {
@@ -129,7 +128,7 @@ int build_tc_tables(Plan* p) {
   rc = upload(&p->tcF_lo, lo);
   if (rc != FNO_OK) return rc;
   p->tc_nch = nch;
-  return launch_fwd2d_tc(p, nullptr, nullptr, nullptr, nullptr, 0, nullptr, true);
+  return launch_fwd2d_tca(p, nullptr, nullptr, 0, nullptr, true);
 }
 
 void free_plan(Plan* p) {

@@ -61,12 +61,9 @@ int launch_inv2d(const Plan* p, const float* Y, const float* addend, float* s_ou
 int setup_transform2d_attrs(const Plan* p);
 int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, float* work,
                     long planes, int cmode, float scale, cudaStream_t st);
-size_t fwd2d_tc_smem_bytes(int nch);
 int launch_fwd2d_tcap(const Plan* p, const float* g, const float* preact, float* ds_out, float* T1, long planes,
                       cudaStream_t st, bool attr_only);
 int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cudaStream_t st, bool attr_only);
-int launch_fwd2d_tc(const Plan* p, const float* x, const float* preact, float* ds_out, float* T1, long planes,
-                    cudaStream_t st, bool attr_only);
 bool layer2d_tc_supported(const Plan* p, int C);
 int setup_layer2d_tc_attrs();
 size_t layer2d_tc_workspace_bytes(const Plan* p, int B, int C);

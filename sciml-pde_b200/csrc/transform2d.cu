@@ -447,256 +447,6 @@ hpass2d_kernel(const float* __restrict__ T1, float2* __restrict__ X, const float
 }
 
 // ------------------------------------------------------------------------------------------
-// K1, TMA-fed persistent form (planes of <= ~68 KB with 16-byte-multiple size, even W, M1T <= 16)
-//
-// One CTA per SM loops over planes.  A producer warp streams whole planes -- a plane is one
-// contiguous run of H*W floats, i.e. ONE cp.async.bulk (SASS UBLKCP) per plane -- into a
-// two-stage shared-memory ring guarded by full/empty mbarriers, so the next plane is in flight for
-// the entire time the current one is being transformed and no consumer warp ever waits on HBM.
-// The consumer warps split a plane's row pairs RG ways (thread = (row group, column pair)), read
-// their rows from shared memory (64-bit conflict-free), and combine the RG partial column
-// transforms through shared memory; the W-axis contraction then runs exactly as in the direct
-// kernel.  Twiddle tables are staged once per CTA instead of once per 3-4 planes.
-// ------------------------------------------------------------------------------------------
-constexpr int TMA_CONSUMERS = 288;   // 9 consumer warps (+ 1 producer warp)
-constexpr int TMA_STAGES = 2;
-
-template <int M1T>
-__global__ void __launch_bounds__(TMA_CONSUMERS + 32, 1)
-fwd2d_tma_kernel(const float* __restrict__ x, float2* __restrict__ X, const float* __restrict__ twH,
-                 const float* __restrict__ twW, int H, int W, int WP, int m1, int m2, int RG, long planes, int cmode,
-                 float scale) {
-  constexpr int TN = 2;
-  constexpr int NJ = Geo<M1T>::NJ;
-  constexpr int JP = Geo<M1T>::JP;
-  const int NP = H / 2 + 1;
-  const int plane_elems = H * W;
-  extern __shared__ __align__(16) float smem[];
-  float* stage_s = smem;                                      // [TMA_STAGES][plane_elems]  (16-B multiple each)
-  float* twH_s = stage_s + (size_t)TMA_STAGES * plane_elems;  // [NP][JP]
-  float* twW_s = twH_s + NP * JP;                             // [2][m2][WP]
-  float* up = twW_s + 2 * m2 * WP;                            // [RG][NJ][WP] partial column transforms; [0] = their sum
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(up + (size_t)RG * NJ * WP);
-  unsigned long long* empty = full + TMA_STAGES;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  constexpr int NCW = TMA_CONSUMERS / 32;
-  if (tid == 0) {
-    for (int s = 0; s < TMA_STAGES; ++s) {
-      mbar_init(full + s, 1);
-      mbar_init(empty + s, NCW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-
-  const long first = blockIdx.x;
-  const long stride = gridDim.x;
-  if (warp == NCW) {
-    // ---- producer: one bulk copy per plane ----------------------------------------------------
-    if (lane == 0) {
-      int it = 0;
-      for (long pl = first; pl < planes; pl += stride, ++it) {
-        const int st = it % TMA_STAGES;
-        mbar_wait(empty + st, ((unsigned)(it / TMA_STAGES) & 1u) ^ 1u);
-        const unsigned bytes = (unsigned)plane_elems * sizeof(float);
-        mbar_arrive_expect_tx(full + st, bytes);
-        bulk_g2s(stage_s + (size_t)st * plane_elems, x + (size_t)pl * plane_elems, bytes, full + st);
-      }
-    }
-    return;
-  }
-
-  // ---- consumers ------------------------------------------------------------------------------
-  {
-    const float4* s4 = reinterpret_cast<const float4*>(twH);
-    float4* d4 = reinterpret_cast<float4*>(twH_s);
-    for (int i = tid; i < NP * JP / 4; i += TMA_CONSUMERS) d4[i] = __ldg(s4 + i);
-    s4 = reinterpret_cast<const float4*>(twW);
-    d4 = reinterpret_cast<float4*>(twW_s);
-    for (int i = tid; i < 2 * m2 * WP / 4; i += TMA_CONSUMERS) d4[i] = __ldg(s4 + i);
-    const int padw = WP - W;                       // pad columns of the partial buffers stay zero forever
-    for (int i = tid; i < RG * NJ * padw; i += TMA_CONSUMERS) {
-      const int r = i / padw;
-      up[r * WP + W + (i - r * padw)] = 0.0f;
-    }
-  }
-  named_bar_sync(1, TMA_CONSUMERS);
-
-  const int tpp = W / TN;
-  const int rg = tid / tpp;                        // row group (>= RG: idle lane of the last warp)
-  const int w0 = (tid - rg * tpp) * TN;
-  const bool worker = rg < RG;
-  const int npairs = (H - 1) / 2;
-  const bool nyq_even = ((W & 1) == 0);
-  // stage-2 decomposition (one plane): tiles x KS slices of the W range
-  const int nJG = (m1 + S2_JT) / S2_JT;
-  const int nKG = (m2 + S2_KT - 1) / S2_KT;
-  const int ntiles = nJG * nKG;
-  const int W4 = WP >> 2;
-  int KS = TMA_CONSUMERS / ntiles;
-  if (KS > W4) KS = W4;
-  while (KS > 1 && (size_t)ntiles * KS * S2_ACC > (size_t)(RG - 1) * NJ * WP) --KS;   // staged in up[1..RG)
-  if (KS < 1) KS = 1;
-  const int cps = (W4 + KS - 1) / KS;
-
-  int it = 0;
-  for (long pl = first; pl < planes; pl += stride, ++it) {
-    const int st = it % TMA_STAGES;
-    const float* __restrict__ ps = stage_s + (size_t)st * plane_elems;
-    mbar_wait(full + st, (unsigned)(it / TMA_STAGES) & 1u);
-
-    // ---- stage 1: this thread's share of the row pairs, from shared memory --------------------
-    float acc[TN][NJ];
-#pragma unroll
-    for (int n = 0; n < TN; ++n)
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) acc[n][j] = 0.0f;
-    if (worker) {
-      const float* __restrict__ xp = ps + w0;
-      if (rg == 0) fold_accumulate_even<M1T, TN>(acc, twH_s, Vec<TN>::ld_plain(xp));
-      if ((H & 1) == 0 && rg == (1 % RG))
-        fold_accumulate_even<M1T, TN>(acc, twH_s + (H / 2) * JP, Vec<TN>::ld_plain(xp + (H / 2) * W));
-      int t = 1 + rg;
-      for (; t + RG <= npairs; t += 2 * RG) {       // two row pairs per trip: their loads overlap the FMAs
-        const Vec<TN> a0 = Vec<TN>::ld_plain(xp + t * W), b0 = Vec<TN>::ld_plain(xp + (H - t) * W);
-        const Vec<TN> a1 = Vec<TN>::ld_plain(xp + (t + RG) * W), b1 = Vec<TN>::ld_plain(xp + (H - t - RG) * W);
-        Vec<TN> e, o;
-#pragma unroll
-        for (int n = 0; n < TN; ++n) { e.v[n] = a0.v[n] + b0.v[n]; o.v[n] = a0.v[n] - b0.v[n]; }
-        fold_accumulate<M1T, TN>(acc, twH_s + t * JP, e, o);
-#pragma unroll
-        for (int n = 0; n < TN; ++n) { e.v[n] = a1.v[n] + b1.v[n]; o.v[n] = a1.v[n] - b1.v[n]; }
-        fold_accumulate<M1T, TN>(acc, twH_s + (t + RG) * JP, e, o);
-      }
-      for (; t <= npairs; t += RG) {
-        const Vec<TN> a0 = Vec<TN>::ld_plain(xp + t * W), b0 = Vec<TN>::ld_plain(xp + (H - t) * W);
-        Vec<TN> e, o;
-#pragma unroll
-        for (int n = 0; n < TN; ++n) { e.v[n] = a0.v[n] + b0.v[n]; o.v[n] = a0.v[n] - b0.v[n]; }
-        fold_accumulate<M1T, TN>(acc, twH_s + t * JP, e, o);
-      }
-    }
-    // the plane buffer is free again as soon as every consumer warp has read its rows
-    __syncwarp();
-    if (lane == 0) mbar_arrive(empty + st);
-    if (worker) {
-      float* urow = up + (size_t)rg * NJ * WP + w0;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        Vec<TN> v;
-#pragma unroll
-        for (int n = 0; n < TN; ++n) v.v[n] = acc[n][j];
-        v.st(urow + j * WP);
-      }
-    }
-    named_bar_sync(1, TMA_CONSUMERS);
-    // ---- sum the RG partial transforms into up[0] (float2 granularity, all threads) -------------
-    if (RG > 1) {
-      const int n2 = NJ * (W / 2);
-      for (int e = tid; e < n2; e += TMA_CONSUMERS) {
-        const int j = e / (W / 2), c = e - j * (W / 2);
-        float2* dst = reinterpret_cast<float2*>(up + (size_t)j * WP) + c;
-        float2 sum = *dst;
-        for (int g = 1; g < RG; ++g) {
-          const float2 v = *(reinterpret_cast<const float2*>(up + ((size_t)g * NJ + j) * WP) + c);
-          sum.x += v.x; sum.y += v.y;
-        }
-        *dst = sum;
-      }
-      named_bar_sync(1, TMA_CONSUMERS);
-    }
-
-    // ---- stage 2: contraction over W (same tiling as the direct kernel, one plane) -------------
-    float pacc[S2_ACC];
-    const bool live = tid < ntiles * KS;
-    const int ks = live ? tid / ntiles : 0;
-    const int tile = live ? tid - ks * ntiles : 0;
-    const int kg = tile % nKG, jg = tile / nKG;
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < S2_ACC; ++i) pacc[i] = 0.f;
-      const float4* A4[S2_JT];
-      const float4* B4[S2_JT];
-#pragma unroll
-      for (int a = 0; a < S2_JT; ++a) {
-        int j = jg * S2_JT + a;
-        if (j > m1) j = m1;
-        A4[a] = reinterpret_cast<const float4*>(up + (size_t)j * WP);
-        B4[a] = reinterpret_cast<const float4*>(up + (size_t)(M1T + (j > 0 ? j : 1)) * WP);
-      }
-      const float4* C4[S2_KT];
-      const float4* S4[S2_KT];
-#pragma unroll
-      for (int b = 0; b < S2_KT; ++b) {
-        int k2 = kg * S2_KT + b;
-        if (k2 >= m2) k2 = m2 - 1;
-        C4[b] = reinterpret_cast<const float4*>(twW_s + (size_t)k2 * WP);
-        S4[b] = reinterpret_cast<const float4*>(twW_s + (size_t)(m2 + k2) * WP);
-      }
-      const int q0 = ks * cps;
-      const int q1 = (q0 + cps < W4) ? q0 + cps : W4;
-      for (int q = q0; q < q1; ++q) {
-        float4 av[S2_JT], bv[S2_JT];
-#pragma unroll
-        for (int a = 0; a < S2_JT; ++a) { av[a] = A4[a][q]; bv[a] = B4[a][q]; }
-#pragma unroll
-        for (int b = 0; b < S2_KT; ++b) {
-          const float4 c = C4[b][q], sn = S4[b][q];
-#pragma unroll
-          for (int a = 0; a < S2_JT; ++a) {
-            float* pp = pacc + (a * S2_KT + b) * 4;
-#define FNO_DOT4(P, U, V) P = fmaf(U.x, V.x, P); P = fmaf(U.y, V.y, P); P = fmaf(U.z, V.z, P); P = fmaf(U.w, V.w, P);
-            FNO_DOT4(pp[0], av[a], c) FNO_DOT4(pp[1], av[a], sn) FNO_DOT4(pp[2], bv[a], c) FNO_DOT4(pp[3], bv[a], sn)
-#undef FNO_DOT4
-          }
-        }
-      }
-    }
-    float* red = up + (size_t)NJ * WP;             // staging in up[1..RG): dead since the partial sum
-    if (KS > 1) {
-      if (live) {
-        float4* r4 = reinterpret_cast<float4*>(red + (size_t)tid * S2_ACC);
-#pragma unroll
-        for (int i = 0; i < S2_ACC / 4; ++i)
-          r4[i] = make_float4(pacc[4 * i], pacc[4 * i + 1], pacc[4 * i + 2], pacc[4 * i + 3]);
-      }
-      named_bar_sync(1, TMA_CONSUMERS);
-    }
-    if (live) {
-      float2* Xp = X + (size_t)pl * (2 * m1) * m2;
-      auto emit_pair = [&](int pi, float4 p4) {
-        const int a = pi / S2_KT, b = pi - a * S2_KT;
-        const int j = jg * S2_JT + a, k2 = kg * S2_KT + b;
-        if (j > m1 || k2 >= m2) return;
-        if (j == 0) { p4.z = 0.f; p4.w = 0.f; }
-        float sc = scale;
-        if (cmode && k2 != 0 && !(nyq_even && 2 * k2 == W)) sc *= 2.0f;
-        if (j < m1) Xp[(size_t)j * m2 + k2] = make_float2((p4.x - p4.w) * sc, -(p4.y + p4.z) * sc);
-        if (j >= 1) Xp[(size_t)(2 * m1 - j) * m2 + k2] = make_float2((p4.x + p4.w) * sc, (p4.z - p4.y) * sc);
-      };
-      if (KS > 1) {
-        for (int pi = ks; pi < S2_JT * S2_KT; pi += KS) {
-          float4 p4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          for (int sl = 0; sl < KS; ++sl) {
-            const float4 v = *reinterpret_cast<const float4*>(red + ((size_t)(sl * ntiles + tile) * S2_ACC) + pi * 4);
-            p4.x += v.x; p4.y += v.y; p4.z += v.z; p4.w += v.w;
-          }
-          emit_pair(pi, p4);
-        }
-      } else {
-#pragma unroll
-        for (int pi = 0; pi < S2_JT * S2_KT; ++pi)
-          emit_pair(pi, make_float4(pacc[4 * pi], pacc[4 * pi + 1], pacc[4 * pi + 2], pacc[4 * pi + 3]));
-      }
-    }
-    // the staging / partial buffers are rewritten by the next plane's stage 1
-    named_bar_sync(1, TMA_CONSUMERS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // K3
 // ------------------------------------------------------------------------------------------
 template <int M1T, int TN, int MAXT, int MINB>
@@ -1074,63 +824,9 @@ static bool misaligned8(const void* a, const void* b = nullptr, const void* c = 
            reinterpret_cast<size_t>(d)) & 7) != 0;
 }
 
-// ---- TMA-fed persistent K1: eligibility and launch ---------------------------------------------
-static int tma_row_groups(const Plan* p) {
-  int rg = TMA_CONSUMERS / (p->W / 2);
-  return rg > 8 ? 8 : rg;
-}
-static size_t fwd_tma_smem_bytes(const Plan* p) {
-  const int NJ = 2 * p->M1T + 1;
-  return sizeof(float) * ((size_t)TMA_STAGES * p->H * p->W + (size_t)p->NP * p->JP + 2ul * p->m2 * p->WP +
-                          (size_t)tma_row_groups(p) * NJ * p->WP) + 2 * TMA_STAGES * sizeof(unsigned long long);
-}
-static bool fwd_tma_eligible(const Plan* p) {
-  // Measured at cfg 1 / batch 128: 150 us vs 101 us for the direct kernel -- one 9-warp consumer group per
-  // SM (all that two 68 KB plane buffers leave room for) cannot fill the issue slots.  Kept as an
-  // opt-in (FNO_K1_TMA=1) until planes are streamed in row chunks so that several groups fit.
-  static const bool enabled = [] { const char* e = std::getenv("FNO_K1_TMA"); return e != nullptr && e[0] == '1'; }();
-  if (!enabled || (p->W & 1) || p->M1T > 16 || ((long)p->H * p->W) % 4 != 0) return false;
-  if (tma_row_groups(p) < 2) return false;
-  const int ntiles = ((p->m1 + S2_JT) / S2_JT) * ((p->m2 + S2_KT - 1) / S2_KT);
-  return ntiles <= TMA_CONSUMERS && fwd_tma_smem_bytes(p) <= kMaxOptinSmem;
-}
-template <int M1T>
-static int launch_fwd_tma(const Plan* p, const float* x, float* X, long planes, int cmode, float scale, cudaStream_t st,
-                          bool attr_only) {
-  if constexpr (M1T <= 16) {
-    auto k = fwd2d_tma_kernel<M1T>;
-    if (attr_only) {
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxOptinSmem) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(fwd2d_tma)");
-      return FNO_OK;
-    }
-    const unsigned grid = (unsigned)(planes < kSMs ? planes : kSMs);
-    k<<<grid, TMA_CONSUMERS + 32, fwd_tma_smem_bytes(p), st>>>(x, reinterpret_cast<float2*>(X), p->twH, p->twW, p->H,
-                                                              p->W, p->WP, p->m1, p->m2, tma_row_groups(p), planes,
-                                                              cmode, scale);
-    count_launch();
-    return check_launch("fwd2d_tma_kernel");
-  } else {
-    set_error("fwd2d_tma: unsupported modes");
-    return FNO_E_ARG;
-  }
-}
-static int dispatch_fwd_tma(const Plan* p, const float* x, float* X, long planes, int cmode, float scale,
-                            cudaStream_t st, bool attr_only) {
-  switch (p->M1T) {
-    case 4: return launch_fwd_tma<4>(p, x, X, planes, cmode, scale, st, attr_only);
-    case 8: return launch_fwd_tma<8>(p, x, X, planes, cmode, scale, st, attr_only);
-    case 12: return launch_fwd_tma<12>(p, x, X, planes, cmode, scale, st, attr_only);
-    case 16: return launch_fwd_tma<16>(p, x, X, planes, cmode, scale, st, attr_only);
-    default: set_error("fwd2d_tma: unsupported modes"); return FNO_E_ARG;
-  }
-}
-
 int launch_fwd2d(const Plan* p, const float* x, const float* preact, float* ds_out, float* X, long planes,
                  int cmode, float scale, cudaStream_t st) {
   if (misaligned8(x, preact, ds_out, X)) { set_error("fwd_transform: tensors must be 8-byte aligned"); return FNO_E_ARG; }
-  if (preact == nullptr && (reinterpret_cast<size_t>(x) & 15) == 0 && planes >= 2 * kSMs && fwd_tma_eligible(p))
-    return dispatch_fwd_tma(p, x, X, planes, cmode, scale, st, false);
   FNO_DISPATCH_M1T(dispatch_fwd, p, x, preact, ds_out, X, planes, cmode, scale, st, false)
 }
 
@@ -1159,18 +855,12 @@ int launch_fwd2d_ws(const Plan* p, const float* x, const float* preact, float* d
   if (work == nullptr || p->tc_nch == 0 || !aligned || planes * p->H < 4096 ||
       sizeof(float) * (size_t)p->NP * p->JP > 48 * 1024)
     return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
-  // plain transform: A operand through TMEM (v2, 44 + 22 us against 100 us for the FP32 kernel at cfg 1).  With
-  // the GELU' premultiply the FP32 kernel stays (174 us; the shared-memory staged v1 measured 262 us and is kept
-  // behind FNO_K1_TC_V1=1 for reference).
-  static const bool v1 = [] { const char* e = std::getenv("FNO_K1_TC_V1"); return e != nullptr && e[0] == '1'; }();
+  // A operand through TMEM (transform2d_tc.cu): 36 + 22 us against 101 us for the FP32 kernel at cfg 1; with the GELU'
+  // premultiply 108 + 22 against 174 us.  FNO_K1P_TC=0 keeps the FP32 kernel for the premultiply form only.
   static const bool premul_tc = [] { const char* e = std::getenv("FNO_K1P_TC"); return e == nullptr || e[0] != '0'; }();
-  int rc = 1;
-  if (!v1) rc = (preact == nullptr) ? launch_fwd2d_tca(p, x, work, planes, st, false)
-                                    : (premul_tc ? launch_fwd2d_tcap(p, x, preact, ds_out, work, planes, st, false) : 1);
-  if (rc == 1) {
-    if (!v1) return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);
-    rc = launch_fwd2d_tc(p, x, preact, ds_out, work, planes, st, false);
-  }
+  int rc = (preact == nullptr) ? launch_fwd2d_tca(p, x, work, planes, st, false)
+                               : (premul_tc ? launch_fwd2d_tcap(p, x, preact, ds_out, work, planes, st, false) : 1);
+  if (rc == 1) return launch_fwd2d(p, x, preact, ds_out, X, planes, cmode, scale, st);   // outside the tensor-core envelope
   if (rc != FNO_OK) return rc;
   switch (p->M1T) {
     case 4: return launch_hpass_t<4>(p, work, X, planes, cmode, scale, st);
@@ -1236,10 +926,6 @@ int setup_transform2d_attrs(const Plan* pc) {
   }
   int rc = setup_fwd_attr(p);
   if (rc != FNO_OK) return rc;
-  if (fwd_tma_eligible(p)) {
-    rc = dispatch_fwd_tma(p, nullptr, nullptr, 0, 0, 0.f, nullptr, true);
-    if (rc != FNO_OK) return rc;
-  }
   return setup_inv_attr(p);
 }
 

@@ -9,34 +9,11 @@ Math (checked by tests against oracle/dft_oracle.py):
 """
 from __future__ import annotations
 
-import os
 from typing import Sequence
 
 import torch
 
 from . import lib
-
-# ---------------------------------------------------------------------------------------------
-# side stream: independent kernels of a Fourier layer (the 1x1-conv bypass next to K1 -> K2, the
-# bypass weight gradient next to K2' -> bypass^T -> K3) overlap on a second stream.  Each of these
-# kernels alone leaves 40-60 % of the issue slots idle waiting on memory (profiles/), so running two
-# of them side by side fills the gaps.  Outputs and scratch are always allocated on the caller's
-# stream and the side stream is joined before they are consumed, so the caching allocator never
-# sees a cross-stream block; under CUDA-graph capture the fork/join become parallel graph branches.
-# ---------------------------------------------------------------------------------------------
-_side_streams: dict = {}
-OVERLAP_FWD = os.environ.get("FNO_OVERLAP_FWD", "0") == "1"   # bypass on a side stream next to K1 / K2 (forward only)
-OVERLAP = os.environ.get("FNO_OVERLAP", "0") == "1"   # measured: no gain at cfg 1 (5.877 vs 5.893 ms), the first kernel fills every SM
-
-
-def _side_stream(device: torch.device) -> torch.cuda.Stream:
-    idx = device.index if device.index is not None else torch.cuda.current_device()
-    s = _side_streams.get(idx)
-    if s is None:
-        s = torch.cuda.Stream(device=idx)
-        _side_streams[idx] = s
-    return s
-
 
 def _plan_for(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> lib.Plan:
     modes = tuple(weights[0].shape[2:])
@@ -106,19 +83,9 @@ class FourierLayerFn(torch.autograd.Function):
             s = torch.empty_like(a) if (training and apply_gelu) else None
             out = lib.layer_inv_fused(plan, Y, a, wl, bl, s_out=s, cmode=1, apply_gelu=bool(apply_gelu))
         else:
-            if OVERLAP or OVERLAP_FWD:
-                main, side = torch.cuda.current_stream(), _side_stream(a.device)
-                lin = torch.empty((a.shape[0], wl.shape[0]) + tuple(a.shape[2:]), dtype=torch.float32, device=a.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    lib.pointwise_fwd(a, wl, bl, out=lin)
-                X = lib.fwd_transform(plan, a)
-                Y = lib.mix_fwd(plan, X, weights)
-                main.wait_stream(side)
-            else:
-                lin = lib.pointwise_fwd(a, wl, bl)
-                X = lib.fwd_transform(plan, a)
-                Y = lib.mix_fwd(plan, X, weights)
+            lin = lib.pointwise_fwd(a, wl, bl)
+            X = lib.fwd_transform(plan, a)
+            Y = lib.mix_fwd(plan, X, weights)
             s = torch.empty_like(lin) if (training and apply_gelu) else None
             out = lib.inv_transform(plan, Y, addend=lin, s_out=s, out=lin, cmode=1, apply_gelu=apply_gelu)
         if training:
@@ -144,7 +111,6 @@ class FourierLayerFn(torch.autograd.Function):
             ds = g
             gY = lib.fwd_transform(plan, g, cmode=1, scale=inv_n)
         gwl = gbl = None
-        forked = False
         ga_lin = None
         if ctx.fused:
             # bypass weight / bias gradient, then K2', then the data gradient K3(gX) + Wl^T dS in one tensor-core pass
@@ -155,26 +121,16 @@ class FourierLayerFn(torch.autograd.Function):
             if gws is None:
                 gws = [None] * len(weights)
             return (ga, gwl if need_wl else None, gbl if (need_bl and ctx.has_bias) else None, None, *gws)
-        if need_ga and need_wl and not OVERLAP:
+        if need_ga and need_wl:
             # weight, bias and data gradient of the bypass in one pass over ds (fno_pointwise_bwd)
             ga_lin, gwl, gbl = lib.pointwise_bwd(ds, a, wl, need_bias=ctx.has_bias)
         elif need_wl or (need_bl and ctx.has_bias):
-            if OVERLAP:
-                main, side = torch.cuda.current_stream(), _side_stream(g.device)
-                bufs = lib.pointwise_wgrad_buffers(ds, a, wl.shape, need_bias=ctx.has_bias)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    gwl, gbl = lib.pointwise_wgrad(ds, a, wl.shape, need_bias=ctx.has_bias, buffers=bufs)
-                forked = True
-            else:
-                gwl, gbl = lib.pointwise_wgrad(ds, a, wl.shape, need_bias=ctx.has_bias)
+            gwl, gbl = lib.pointwise_wgrad(ds, a, wl.shape, need_bias=ctx.has_bias)
         gX, gws = lib.mix_bwd(plan, X, gY, weights, need_gx=need_ga, need_gw=need_gw)
         ga = None
         if need_ga:
             ga = ga_lin if ga_lin is not None else lib.pointwise_fwd(ds, wl, None, transpose=True)
             lib.inv_transform(plan, gX, addend=ga, out=ga, cmode=0, scale=1.0)
-        if forked:
-            main.wait_stream(side)
         if gws is None:
             gws = [None] * len(weights)
         return (ga, gwl if need_wl else None, gbl if (need_bl and ctx.has_bias) else None, None, *gws)
