@@ -223,6 +223,22 @@ int fno_window_gather(const float* traj, const long long* traj_idx, const int* t
                       float* yy, int B, long npix, int T, int V, int initial_step, int rollout,
                       fno_stream_t stream);
 
+/* ---- on-device evaluation -------------------------------------------------------- */
+/* metric_func(pred, target, if_mean=True, Lx, Ly, Lz, iLow, iHigh) of pdebench/models/metrics.py:164-306 for fields in the
+ * loaders' layout pred, target [B, nx, ny(, nz), T, V] (2-D: nz = 1):
+ *   out[0..7] = RMSE, normalised RMSE, RMSE of the conserved variables, maximum error, RMSE at the boundaries,
+ *               RMSE in Fourier space (low / middle / high band; NaN for an empty band, as the reference's empty mean)
+ *   out[8+t]  = sqrt(mean over (b, grid, v) of (pred-target)^2) per time step: the `val_l2_time` term of metrics.py:386-393
+ * `work`: fno_metric_workspace_bytes(...) bytes of device scratch (zeroed by the call). */
+size_t fno_metric_workspace_bytes(int B, int nx, int ny, int nz, int T, int V);
+int fno_metric_func(const float* pred, const float* target, void* work, float* out, int B, int nx, int ny,
+                    int nz, int T, int V, float Lx, float Ly, float Lz, int iLow, int iHigh,
+                    fno_stream_t stream);
+/* The autoregressive window shift of the rollout loop, `xx = torch.cat((xx[..., 1:, :], pred), dim=-2)`
+ * (metrics.py:344): xx, xx_out [points, T0, V], pred [points, 1, V]; xx_out != xx. */
+int fno_window_shift(const float* xx, const float* pred, float* xx_out, long points, int T0, int V,
+                     fno_stream_t stream);
+
 /* ---- step tail: loss, gradient clipping, Adam, LR schedule --------------------- */
 /* nrmse(out, target).mean() of fno/train.py:34-40,:266-267 for out / target [B, P, V] (P = pixels x
  * output steps): loss[0] = mean_{b,v} ( mean_p (out-y)^2 / (1e-7 + mean_p y^2) ).

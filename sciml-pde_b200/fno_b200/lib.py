@@ -54,6 +54,9 @@ def load():
             "fno_plan2d_create": (i, [i, i, i, i, i, vpp]),
             "fno_plan3d_create": (i, [i, i, i, i, i, i, i, vpp]),
             "fno_window_gather": (i, [vp, vp, vp, vp, vp, i, l, i, i, i, i, vp]),
+            "fno_metric_workspace_bytes": (C.c_size_t, [i, i, i, i, i, i]),
+            "fno_metric_func": (i, [vp, vp, vp, vp, i, i, i, i, i, i, f, f, f, i, i, vp]),
+            "fno_window_shift": (i, [vp, vp, vp, l, i, i, vp]),
             "fno_set_math_mode": (i, [i]),
             "fno_get_math_mode": (i, []),
             "fno_plan_destroy": (i, [vp]),
@@ -115,6 +118,7 @@ EXPORTED_SYMBOLS = (
     "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
+    "fno_metric_workspace_bytes", "fno_metric_func", "fno_window_shift",
 )
 
 
@@ -608,3 +612,41 @@ def window_gather(traj: torch.Tensor, traj_idx: torch.Tensor, t_start: torch.Ten
                                     yy.data_ptr(), B, npix, T, V, initial_step, rollout, _stream()),
            "fno_window_gather")
     return xx, yy
+
+
+@_on_tensor_device
+def metric_func(pred: torch.Tensor, target: torch.Tensor, Lx: float = 1.0, Ly: float = 1.0, Lz: float = 1.0,
+                iLow: int = 4, iHigh: int = 12) -> torch.Tensor:
+    """pred, target [B, nx, ny(, nz), T, V] f32 -> device tensor [8 + T]: RMSE, nRMSE, CSV, Max, BD, F_low, F_mid, F_high,
+    then the per-time-step RMSE (metrics.py:164-306 with if_mean=True, :386-393).  No host synchronisation."""
+    _require(pred, torch.float32, "pred")
+    _require(target, torch.float32, "target")
+    if pred.shape != target.shape or pred.dim() not in (5, 6):
+        raise FnoError(f"metric_func: pred / target must be equal-shaped [B, nx, ny(, nz), T, V], got {tuple(pred.shape)} / {tuple(target.shape)}")
+    B, nx, ny = pred.shape[:3]
+    nz = pred.shape[3] if pred.dim() == 6 else 1
+    T, V = pred.shape[-2:]
+    L = load()
+    nbytes = L.fno_metric_workspace_bytes(B, nx, ny, nz, T, V)
+    work = torch.empty(nbytes, dtype=torch.uint8, device=pred.device)
+    out = torch.empty(8 + T, dtype=torch.float32, device=pred.device)
+    _check(L.fno_metric_func(pred.data_ptr(), target.data_ptr(), work.data_ptr(), out.data_ptr(), B, nx, ny, nz, T, V,
+                             float(Lx), float(Ly), float(Lz), int(iLow), int(iHigh), _stream()), "fno_metric_func")
+    return out
+
+
+@_on_tensor_device
+def window_shift(xx: torch.Tensor, pred: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """xx [..., T0, V], pred [..., 1, V] -> cat(xx[..., 1:, :], pred) (metrics.py:344) in one kernel."""
+    _require(xx, torch.float32, "xx")
+    _require(pred, torch.float32, "pred")
+    T0, V = xx.shape[-2:]
+    if tuple(pred.shape) != tuple(xx.shape[:-2]) + (1, V):
+        raise FnoError(f"window_shift: pred must be {tuple(xx.shape[:-2]) + (1, V)}, got {tuple(pred.shape)}")
+    if out is None:
+        out = torch.empty_like(xx)
+    _require(out, torch.float32, "out")
+    points = xx.numel() // (T0 * V)
+    _check(load().fno_window_shift(xx.data_ptr(), pred.data_ptr(), out.data_ptr(), points, T0, V, _stream()),
+           "fno_window_shift")
+    return out
