@@ -223,6 +223,23 @@ int fno_window_gather(const float* traj, const long long* traj_idx, const int* t
                       float* yy, int B, long npix, int T, int V, int initial_step, int rollout,
                       fno_stream_t stream);
 
+/* ---- SpectralConv1d (named by north_star; the reference tree has no 1-D layer, so this follows the 2-D layer's
+ * conventions, fno/fno.py:35-92, one dimension down) ---------------------------------------------------------------- */
+/* X[r, k] = scale * c_k * sum_n x[r, n] exp(-2 pi i k n / N), k < m: pruned torch.fft.rfft(x)[..., :m]; with cmode = 1,
+ * scale = 1/N the backward of fno_sc1d_inv_transform.  x [rows, N] f32, X [rows, m] complex64 interleaved. */
+int fno_sc1d_fwd_transform(const float* x, float* X, long rows, int N, int m, int cmode, float scale,
+                           fno_stream_t stream);
+/* y[r, n] = scale * sum_k c_k Re(Y[r, k] exp(+2 pi i k n / N)) (+ addend): torch.fft.irfft of the zero-padded spectrum
+ * (cmode = 1, scale = 1/N: c_0 = 1, c_k = 2, c_{N/2} = 1, Im of DC / Nyquist ignored); cmode = 0, scale = 1: the backward
+ * of fno_sc1d_fwd_transform. */
+int fno_sc1d_inv_transform(const float* Y, const float* addend, float* y, long rows, int N, int m, int cmode,
+                           float scale, fno_stream_t stream);
+/* einsum("bix,iox->box") over the m retained modes (X [B, Ci, m], W [Ci, Co, m], Y [B, Co, m], complex64) and its
+ * gradients gX = sum_o gY conj(W), gW = sum_b conj(X) gY (either may be NULL). */
+int fno_mix1d_fwd(const float* X, const float* W, float* Y, int B, int Ci, int Co, int m, fno_stream_t stream);
+int fno_mix1d_bwd(const float* X, const float* gY, const float* W, float* gX, float* gW, int B, int Ci, int Co,
+                  int m, fno_stream_t stream);
+
 /* ---- on-device evaluation -------------------------------------------------------- */
 /* metric_func(pred, target, if_mean=True, Lx, Ly, Lz, iLow, iHigh) of pdebench/models/metrics.py:164-306 for fields in the
  * loaders' layout pred, target [B, nx, ny(, nz), T, V] (2-D: nz = 1):

@@ -280,3 +280,34 @@ def rel_err(got, ref) -> float:
     if denom == 0.0:
         return float(np.max(np.abs(got)))
     return float(np.max(np.abs(got - ref)) / denom)
+
+
+# ------------------------------------------------------------------------------------------------
+# SpectralConv1d.  PARITY UNPINNED against the reference: /root/reference has no 1-D layer; north_star names
+# it, so the oracle states the 2-D layer's algorithm (fno/fno.py:70-92) one dimension down,
+#     y = irfft(pad(einsum("bix,iox->box", rfft(x)[..., :m], W)), n = N),
+# as dense DFT products in float64, and tests/test_spectral1d_gpu.py additionally cross-checks it against torch.fft.
+# ------------------------------------------------------------------------------------------------
+def spectral_conv1d_forward(x: np.ndarray, w: np.ndarray, return_saved: bool = False):
+    """x [B, Ci, N] real, w [Ci, Co, m] complex -> [B, Co, N]."""
+    n, m = x.shape[-1], w.shape[-1]
+    F = dft_half_cols(n, m)                                   # [N, m]: exp(-2 pi i q w / N)
+    X = x.astype(np.float64) @ F                              # pruned rfft
+    Y = np.einsum("bik,iok->bok", X, w.astype(np.complex128))
+    c = c2r_weights(n, m)
+    y = np.real((Y * c) @ np.conj(F).T) / n
+    # torch.fft.irfft ignores Im of the DC (and Nyquist) column: Re(Y e^{i0}) does that by construction
+    return (y, X) if return_saved else y
+
+
+def spectral_conv1d_backward(x: np.ndarray, w: np.ndarray, g: np.ndarray):
+    """Gradients (gx, gw) in PyTorch's complex convention (dL/dRe + i dL/dIm)."""
+    n, m = x.shape[-1], w.shape[-1]
+    F = dft_half_cols(n, m)
+    _, X = spectral_conv1d_forward(x, w, return_saved=True)
+    gY = (g.astype(np.float64) @ F) * (c2r_weights(n, m) / n)
+    wc = w.astype(np.complex128)
+    gX = np.einsum("bok,iok->bik", gY, np.conj(wc))
+    gw = np.einsum("bik,bok->iok", np.conj(X), gY)
+    gx = np.real(gX @ np.conj(F).T)
+    return gx, gw

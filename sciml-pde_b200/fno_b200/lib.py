@@ -54,6 +54,10 @@ def load():
             "fno_plan2d_create": (i, [i, i, i, i, i, vpp]),
             "fno_plan3d_create": (i, [i, i, i, i, i, i, i, vpp]),
             "fno_window_gather": (i, [vp, vp, vp, vp, vp, i, l, i, i, i, i, vp]),
+            "fno_sc1d_fwd_transform": (i, [vp, vp, l, i, i, i, f, vp]),
+            "fno_sc1d_inv_transform": (i, [vp, vp, vp, l, i, i, i, f, vp]),
+            "fno_mix1d_fwd": (i, [vp, vp, vp, i, i, i, i, vp]),
+            "fno_mix1d_bwd": (i, [vp, vp, vp, vp, vp, i, i, i, i, vp]),
             "fno_metric_workspace_bytes": (C.c_size_t, [i, i, i, i, i, i]),
             "fno_metric_func": (i, [vp, vp, vp, vp, i, i, i, i, i, i, f, f, f, i, i, vp]),
             "fno_window_shift": (i, [vp, vp, vp, l, i, i, vp]),
@@ -119,6 +123,7 @@ EXPORTED_SYMBOLS = (
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
     "fno_metric_workspace_bytes", "fno_metric_func", "fno_window_shift",
+    "fno_sc1d_fwd_transform", "fno_sc1d_inv_transform", "fno_mix1d_fwd", "fno_mix1d_bwd",
 )
 
 
@@ -650,3 +655,57 @@ def window_shift(xx: torch.Tensor, pred: torch.Tensor, out: Optional[torch.Tenso
     _check(load().fno_window_shift(xx.data_ptr(), pred.data_ptr(), out.data_ptr(), points, T0, V, _stream()),
            "fno_window_shift")
     return out
+
+
+# ---- SpectralConv1d ------------------------------------------------------------------------------------------
+@_on_tensor_device
+def fwd_transform1d(x: torch.Tensor, modes: int, *, cmode: int = 0, scale: float = 1.0) -> torch.Tensor:
+    """x [..., N] f32 -> [..., modes] complex64 (pruned rfft; cmode=1, scale=1/N: backward of inv_transform1d)."""
+    _require(x, torch.float32, "x")
+    N = x.shape[-1]
+    X = torch.empty(tuple(x.shape[:-1]) + (modes,), dtype=torch.complex64, device=x.device)
+    _check(load().fno_sc1d_fwd_transform(x.data_ptr(), X.data_ptr(), x.numel() // N, N, modes, cmode, scale, _stream()),
+           "fno_sc1d_fwd_transform")
+    return X
+
+
+@_on_tensor_device
+def inv_transform1d(Y: torch.Tensor, n: int, *, addend: Optional[torch.Tensor] = None, cmode: int = 1,
+                    scale: Optional[float] = None) -> torch.Tensor:
+    """Y [..., modes] complex64 -> [..., n] f32 (zero-padded irfft; cmode=0, scale=1: backward of fwd_transform1d)."""
+    _require(Y, torch.complex64, "Y")
+    m = Y.shape[-1]
+    y = torch.empty(tuple(Y.shape[:-1]) + (n,), dtype=torch.float32, device=Y.device)
+    if addend is not None:
+        _require(addend, torch.float32, "addend")
+        if addend.shape != y.shape:
+            raise FnoError("inv_transform1d: addend shape mismatch")
+    _check(load().fno_sc1d_inv_transform(Y.data_ptr(), _ptr(addend), y.data_ptr(), Y.numel() // m, n, m, cmode,
+                                         1.0 / n if scale is None else scale, _stream()), "fno_sc1d_inv_transform")
+    return y
+
+
+@_on_tensor_device
+def mix1d_fwd(X: torch.Tensor, W: torch.Tensor) -> torch.Tensor:
+    _require(X, torch.complex64, "X")
+    _require(W, torch.complex64, "W")
+    B, Ci, m = X.shape
+    if W.shape[0] != Ci or W.shape[2] != m:
+        raise FnoError(f"mix1d: X {tuple(X.shape)} does not match W {tuple(W.shape)}")
+    Y = torch.empty((B, W.shape[1], m), dtype=torch.complex64, device=X.device)
+    _check(load().fno_mix1d_fwd(X.data_ptr(), W.data_ptr(), Y.data_ptr(), B, Ci, W.shape[1], m, _stream()), "fno_mix1d_fwd")
+    return Y
+
+
+@_on_tensor_device
+def mix1d_bwd(X: torch.Tensor, gY: torch.Tensor, W: torch.Tensor, need_gx: bool = True, need_gw: bool = True):
+    _require(gY, torch.complex64, "gY")
+    _require(X, torch.complex64, "X")
+    _require(W, torch.complex64, "W")
+    B, Ci, m = X.shape
+    Co = W.shape[1]
+    gX = torch.empty_like(X) if need_gx else None
+    gW = torch.empty_like(W) if need_gw else None
+    _check(load().fno_mix1d_bwd(X.data_ptr(), gY.data_ptr(), W.data_ptr(), _ptr(gX), _ptr(gW), B, Ci, Co, m, _stream()),
+           "fno_mix1d_bwd")
+    return gX, gW

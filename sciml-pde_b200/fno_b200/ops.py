@@ -194,3 +194,36 @@ def lift(x, grid, W0, b0, padding: int):
 
 def head(h, W1, b1, W2, b2, stats, geo):
     return HeadFn.apply(h, W1, b1, W2, b2, stats, geo)
+
+
+class SpectralConv1dFn(torch.autograd.Function):
+    """y = irfft(pad(einsum(rfft(x)[..., :m], W)), n = N) for x [B, Ci, N], W [Ci, Co, m] complex64 (the 2-D layer's
+    convention, fno/fno.py:70-92, one dimension down).  Backward mirrors each kernel: K1' = c_k / N * pruned rfft of g,
+    K2' = the two mixing gradients, K3' = unweighted inverse of gX."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x, w = x.contiguous(), w.contiguous()
+        m = w.shape[2]
+        X = lib.fwd_transform1d(x, m)
+        Y = lib.mix1d_fwd(X, w)
+        ctx.save_for_backward(X, w)
+        ctx.n = x.shape[-1]
+        return lib.inv_transform1d(Y, x.shape[-1])
+
+    @staticmethod
+    def backward(ctx, g):
+        X, w = ctx.saved_tensors
+        n = ctx.n
+        gY = lib.fwd_transform1d(g.contiguous(), w.shape[2], cmode=1, scale=1.0 / n)
+        gX, gW = lib.mix1d_bwd(X, gY, w, need_gx=ctx.needs_input_grad[0], need_gw=ctx.needs_input_grad[1])
+        gx = lib.inv_transform1d(gX, n, cmode=0, scale=1.0) if gX is not None else None
+        return gx, gW
+
+
+def spectral_conv1d(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    if x.dim() != 3 or w.dim() != 3 or x.shape[1] != w.shape[0]:
+        raise lib.FnoError(f"spectral_conv1d: expected x [B, Ci, N] and W [Ci, Co, m], got {tuple(x.shape)}, {tuple(w.shape)}")
+    if w.shape[2] > x.shape[-1] // 2 + 1:
+        raise lib.FnoError(f"spectral_conv1d: modes1 = {w.shape[2]} exceeds N/2 + 1 = {x.shape[-1] // 2 + 1}")
+    return SpectralConv1dFn.apply(x, w)

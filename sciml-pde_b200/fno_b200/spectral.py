@@ -39,6 +39,40 @@ class _SpectralConvBase(nn.Module):
         return ops.spectral_conv(x, self._weights())
 
 
+class SpectralConv1d(_SpectralConvBase):
+    """1-D Fourier layer: pruned rfft -> per-mode channel mixing -> zero-padded irfft.  Named by the task's north_star;
+    the reference tree has no 1-D layer, so constructor, parameter name / layout (`weights1` complex64 `[Ci, Co, modes1]`,
+    `scale * rand`) and forward follow `SpectralConv2d_fast` (fno/fno.py:35-92) one dimension down."""
+    _ncorners = 1
+
+    def __init__(self, in_channels, out_channels, modes1):
+        super().__init__(in_channels, out_channels, modes1)
+
+    def compl_mul1d(self, input, weights):
+        """(batch, in, x), (in, out, x) -> (batch, out, x)"""
+        if not input.is_cuda:
+            raise lib.FnoError("compl_mul1d runs on CUDA sm_100a only")
+        return _Mix1dFn.apply(input, weights)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if not x.is_cuda:
+            raise lib.FnoError(f"SpectralConv1d runs on CUDA sm_100a only (no CPU fallback); input is on {x.device}")
+        return ops.spectral_conv1d(x, self.weights1)
+
+
+class _Mix1dFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, w):
+        X, w = X.contiguous(), w.contiguous()
+        ctx.save_for_backward(X, w)
+        return lib.mix1d_fwd(X, w)
+
+    @staticmethod
+    def backward(ctx, g):
+        X, w = ctx.saved_tensors
+        return lib.mix1d_bwd(X, g.contiguous(), w, need_gx=ctx.needs_input_grad[0], need_gw=ctx.needs_input_grad[1])
+
+
 class SpectralConv2d_fast(_SpectralConvBase):
     """2-D Fourier layer: pruned rfft2 -> per-mode channel mixing -> zero-padded irfft2."""
     _ncorners = 2
