@@ -78,7 +78,7 @@ pointwise_kernel(const float* __restrict__ in, const float* __restrict__ Wm, con
 // the one-load-at-a-time loop above exposes (profiles/r1_b: 183 registers, 12 % occupancy).
 constexpr int PW_CH = 20;
 
-template <int OT, bool TRANSPOSE>
+template <int OT, bool TRANSPOSE, int CH = PW_CH>
 __global__ void __launch_bounds__(256, 2)
 pointwise2_kernel(const float* __restrict__ in, const float* __restrict__ Wm, const float* __restrict__ bias,
                   float* __restrict__ out, int Cin, int Cout, int Co, int Ci, long N2) {
@@ -103,13 +103,13 @@ pointwise2_kernel(const float* __restrict__ in, const float* __restrict__ Wm, co
 #pragma unroll
   for (int oo = 0; oo < OT; ++oo) acc[oo] = make_float2(bs[oo], bs[oo]);
   const float2* __restrict__ ip = reinterpret_cast<const float2*>(in) + (size_t)b * Cin * N2 + p;
-  for (int s0 = 0; s0 < Cin; s0 += PW_CH) {
-    float2 xv[PW_CH];
+  for (int s0 = 0; s0 < Cin; s0 += CH) {
+    float2 xv[CH];
 #pragma unroll
-    for (int u = 0; u < PW_CH; ++u)
+    for (int u = 0; u < CH; ++u)
       xv[u] = (s0 + u < Cin) ? __ldg(ip + (size_t)(s0 + u) * N2) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int u = 0; u < PW_CH; ++u) {
+    for (int u = 0; u < CH; ++u) {
       if (s0 + u < Cin) {
         const float4* wrow = reinterpret_cast<const float4*>(ws + (s0 + u) * OT);
 #pragma unroll
@@ -131,7 +131,7 @@ pointwise2_kernel(const float* __restrict__ in, const float* __restrict__ Wm, co
   }
 }
 
-template <int OT>
+template <int OT, int CH = PW_CH>
 int launch_pw2(const float* in, const float* Wm, const float* bias, float* out, int B, int Co, int Ci, long N,
                int transpose, cudaStream_t st) {
   const int Cin = transpose ? Co : Ci;
@@ -140,9 +140,9 @@ int launch_pw2(const float* in, const float* Wm, const float* bias, float* out, 
   dim3 grid((unsigned)((N2 + 255) / 256), (Cout + OT - 1) / OT, B);
   const size_t smem = sizeof(float) * ((size_t)Cin * OT + OT);
   if (transpose)
-    pointwise2_kernel<OT, true><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
+    pointwise2_kernel<OT, true, CH><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
   else
-    pointwise2_kernel<OT, false><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
+    pointwise2_kernel<OT, false, CH><<<grid, 256, smem, st>>>(in, Wm, bias, out, Cin, Cout, Co, Ci, N2);
   count_launch();
   return check_launch("pointwise2_kernel");
 }
@@ -461,6 +461,118 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Wide-channel weight gradient (20 < max(Co, Ci) <= 64: BASELINE configs[2], width 64).  The T x T-per-warp kernels above
+// need Co/T x Ci/T warps per CTA; at width 64 that is 49 tiles, i.e. 7 CTA groups that each re-read the same slabs.  Here a
+// CTA owns the WHOLE 64 x 64 output: 4 pixel groups x 64 threads, thread = 8 x 8 register tile (rows og + 8 j, columns
+// ig + 8 j: consecutive threads touch consecutive shared-memory rows, whose 272-byte pitch spreads them over all banks), 16
+// LDS.128 per 256 FMA, slabs of 64 pixels through a 2-stage cp.async ring, two CTAs per SM.  The pixel groups are summed
+// through shared memory at the end; per-CTA partials go through wgrad_reduce_kernel like the other forms.
+// ------------------------------------------------------------------------------------------
+constexpr int WW_KT = 64;          // pixels per slab
+constexpr int WW_P = WW_KT + 4;    // row pitch (floats)
+constexpr int WW_C = 64;           // padded channels
+constexpr int WW_THREADS = 256;
+
+__global__ void __launch_bounds__(WW_THREADS, 2)
+wgrad_wide_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co, int Ci,
+                  long N, int slabs_per_sample, long total_slabs, long slabs_per_cta) {
+  extern __shared__ __align__(16) float sm[];        // 2 stages x [2 * WW_C][WW_P]  (ds rows, then a rows)
+  constexpr int STAGE = 2 * WW_C * WW_P;
+  const int tid = threadIdx.x;
+  const int kg = tid >> 6, og = (tid >> 3) & 7, ig = tid & 7;
+  long s_begin = (long)blockIdx.x * slabs_per_cta;
+  long s_end = s_begin + slabs_per_cta;
+  if (s_end > total_slabs) s_end = total_slabs;
+  // rows beyond Co / Ci are never written by the copies: zero them once
+  for (int i = tid; i < 2 * STAGE; i += WW_THREADS) sm[i] = 0.f;
+  __syncthreads();
+
+  float acc[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  float accb = 0.f;                                  // bias: thread = (row tid / 4, 16-pixel chunk tid % 4)
+
+  auto issue = [&](long slab, int stage) {
+    float* dst = sm + (size_t)stage * STAGE;
+    const long b = slab / slabs_per_sample;
+    const long k0 = (slab - b * slabs_per_sample) * WW_KT;
+    const float* dsb = ds + (size_t)b * Co * N;
+    const float* ab = a + (size_t)b * Ci * N;
+    for (int idx = tid; idx < 2 * WW_C * (WW_KT / 4); idx += WW_THREADS) {
+      const int c = idx / (WW_KT / 4), q = idx - c * (WW_KT / 4);
+      const bool is_ds = c < WW_C;
+      const int ch = is_ds ? c : c - WW_C;
+      if (ch >= (is_ds ? Co : Ci)) continue;
+      const long k = k0 + 4 * q;
+      const float* src = (is_ds ? dsb : ab) + (size_t)ch * N + k;
+      const long left = (N - k) * 4;
+      const int nb = left >= 16 ? 16 : (left > 0 ? (int)left : 0);
+      cp_async16(dst + c * WW_P + 4 * q, nb > 0 ? src : ds, nb);
+    }
+    cp_async_commit();
+  };
+
+  if (s_begin < s_end) issue(s_begin, 0);
+  for (long slab = s_begin; slab < s_end; ++slab) {
+    const int stage = (int)((slab - s_begin) & 1);
+    if (slab + 1 < s_end) {
+      issue(slab + 1, stage ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* ds_s = sm + (size_t)stage * STAGE;
+    const float* a_s = ds_s + WW_C * WW_P;
+    {
+      const float4* br = reinterpret_cast<const float4*>(ds_s + (tid >> 2) * WW_P + (tid & 3) * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = br[q];
+        accb += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+#pragma unroll
+    for (int st = 0; st < WW_KT / 16; ++st) {
+      const int px = kg * (WW_KT / 4) + st * 4;
+      float4 dv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dv[j] = *reinterpret_cast<const float4*>(ds_s + (og + 8 * j) * WW_P + px);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float4 av = *reinterpret_cast<const float4*>(a_s + (ig + 8 * c) * WW_P + px);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          acc[r][c] = fmaf(dv[r].x, av.x, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].y, av.y, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].z, av.z, acc[r][c]);
+          acc[r][c] = fmaf(dv[r].w, av.w, acc[r][c]);
+        }
+      }
+    }
+    __syncthreads();  // the stage is refilled by the next iteration's issue()
+  }
+  // combine the 4 pixel groups: red[kg][o][i] (64 KB of the 68 KB ring), bias partials behind it
+  float* red = sm;
+  float* redb = sm + 4 * WW_C * WW_C;                 // [64 rows][4 chunks]
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) red[(kg * WW_C + og + 8 * r) * WW_C + ig + 8 * c] = acc[r][c];
+  redb[tid] = accb;
+  __syncthreads();
+  float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
+  for (int e = tid; e < WW_C * WW_C; e += WW_THREADS) {
+    const int o = e / WW_C, i = e - o * WW_C;
+    if (o < Co && i < Ci)
+      pp[(size_t)o * (Ci + 1) + i] = (red[e] + red[WW_C * WW_C + e]) + (red[2 * WW_C * WW_C + e] + red[3 * WW_C * WW_C + e]);
+  }
+  if (tid < Co) pp[(size_t)tid * (Ci + 1) + Ci] = (redb[4 * tid] + redb[4 * tid + 1]) + (redb[4 * tid + 2] + redb[4 * tid + 3]);
+}
+
 // one warp per output element: lanes stride the per-CTA partials, fixed-order shuffle tree
 __global__ void __launch_bounds__(128)
 wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gW, float* __restrict__ gb, int nparts,
@@ -591,6 +703,30 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
     if (rc2 != FNO_OK) return rc2;
     const int total2 = Co * (Ci + 1);
     wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas2 * KH, Co, Ci);
+    count_launch();
+    return check_launch("wgrad_reduce_kernel");
+  }
+  if (aligned && ygroups > 1 && Co <= WW_C && Ci <= WW_C) {
+    // wide channels: one CTA owns the whole Co x Ci output (wgrad_wide_kernel)
+    const size_t smemw = sizeof(float) * 2ul * 2 * WW_C * WW_P;
+    static_assert(sizeof(float) * (4ul * WW_C * WW_C + WW_THREADS) <= sizeof(float) * 2ul * 2 * WW_C * WW_P, "reduce buffer fits the ring");
+    static PerDeviceOnce attrw_done;
+    if (attrw_done.need()) {
+      if (cudaFuncSetAttribute(wgrad_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemw) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(wgrad_wide)");
+      attrw_done.mark();
+    }
+    const int spsw = (int)((N + WW_KT - 1) / WW_KT);
+    const long totalw = (long)B * spsw;
+    long ctasw = totalw < WG_CTAS ? totalw : WG_CTAS;
+    const long spcw = (totalw + ctasw - 1) / ctasw;
+    ctasw = (totalw + spcw - 1) / spcw;
+    wgrad_wide_kernel<<<(unsigned)ctasw, WW_THREADS, smemw, st>>>(ds, a, part, Co, Ci, N, spsw, totalw, spcw);
+    count_launch();
+    int rcw = check_launch("wgrad_wide_kernel");
+    if (rcw != FNO_OK) return rcw;
+    const int totalo = Co * (Ci + 1);
+    wgrad_reduce_kernel<<<(totalo * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctasw, Co, Ci);
     count_launch();
     return check_launch("wgrad_reduce_kernel");
   }
