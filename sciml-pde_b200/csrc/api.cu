@@ -249,7 +249,11 @@ int fno_plan_destroy(fno_plan* plan) {
 size_t fno_plan_workspace_bytes(const fno_plan* plan, long planes) {
   const Plan* p = P(plan);
   if (p == nullptr || p->nd != 3 || planes <= 0) return 0;
-  return sizeof(float) * 2ul * (size_t)planes * p->D1 * (2 * p->m1) * p->m2;
+  // per-slice plane spectra (forward: S, inverse: Z), then -- when the inner planes are inside the tensor-core envelope
+  // of K1 -- the T1 scratch of its W-axis GEMM (16-byte aligned: the first part is a multiple of 16 floats)
+  const size_t spectra = (sizeof(float) * 2ul * (size_t)planes * p->D1 * (2 * p->m1) * p->m2 + 255) & ~(size_t)255;
+  const size_t t1 = p->tc_nch ? sizeof(float) * (size_t)planes * p->D1 * p->H * ((2 * p->m2 + 3) & ~3) : 0;
+  return spectra + t1;
 }
 
 int fno_sc2d_fwd_transform(const fno_plan* plan, const float* x, const float* preact, float* ds_out, float* X,
@@ -286,7 +290,10 @@ int fno_sc3d_fwd_transform(const fno_plan* plan, const float* x, const float* pr
   if (!p || p->nd != 3 || !x || !X || !work || planes <= 0) { set_error("fno_sc3d_fwd_transform: bad argument"); return FNO_E_ARG; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* S = static_cast<float*>(work);
-  int rc = launch_fwd2d(p, x, preact, ds_out, S, planes * p->D1, cmode, scale, st);
+  const size_t spectra = (sizeof(float) * 2ul * (size_t)planes * p->D1 * (2 * p->m1) * p->m2 + 255) & ~(size_t)255;
+  float* T1 = p->tc_nch ? reinterpret_cast<float*>(static_cast<char*>(work) + spectra) : nullptr;
+  // inner planes: tcgen05 W-axis GEMM + strided-axis fold when eligible (launch_fwd2d_ws falls back to the FP32 kernel)
+  int rc = launch_fwd2d_ws(p, x, preact, ds_out, S, T1, planes * p->D1, cmode, scale, st);
   if (rc != FNO_OK) return rc;
   return launch_axis_fwd(p, S, X, planes, (long)(2 * p->m1) * p->m2, st);
 }
