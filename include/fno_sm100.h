@@ -54,9 +54,13 @@ void fno_shutdown(void);                       /* destroys every live plan */
  * results within the fp32-mode tolerance (<= 1e-5 relative).  FNO_MATH_TF32: a single kind::tf32 pass
  * (10-bit mantissa operands, fp32 accumulate); stated bound <= 2e-3 relative on the outputs and gradients of
  * the projection head and of the forward transform's truncated-DFT GEMM (tests/test_kernels_gpu.py::
- * test_head_tf32_mode, ::test_fwd_transform_tf32_mode).  The FP32 CUDA-core kernels are not affected.  Returns the previous mode, or a negative error code.                          */
+ * test_head_tf32_mode, ::test_fwd_transform_tf32_mode).  FNO_MATH_BF16: every MMA operand is rounded to bfloat16
+ * (8-bit significand), one pass, fp32 accumulate -- the arithmetic of a bf16 tensor-core MMA, issued on the tf32 datapath
+ * (bf16 values are tf32 values), so it runs at tf32-mode speed; stated bound <= 2e-2 relative (::test_*_bf16_mode).
+ * The FP32 CUDA-core kernels are not affected.  Returns the previous mode, or a negative error code.                   */
 #define FNO_MATH_FP32 0
 #define FNO_MATH_TF32 1
+#define FNO_MATH_BF16 2
 int fno_set_math_mode(int mode);
 int fno_get_math_mode(void);
 

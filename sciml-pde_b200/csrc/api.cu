@@ -109,21 +109,26 @@ void split_tf32_host(float x, float& hi, float& lo) {
 // F[q][w] for the tensor-core W-axis stage: q < m2 cos, m2 <= q < 2*m2 sin, in the K-major UMMA B layout
 //   (q % 8) * 16 + (q / 8) * (nch * 128) + (w / 4) * 128 + (w % 4) * 4  bytes, 32 rows, nch chunks
 int build_tc_tables(Plan* p) {
-  p->tcF_hi = p->tcF_lo = nullptr;
+  p->tcF_hi = p->tcF_lo = p->tcF_bf = nullptr;
   p->tc_nch = 0;
   const int W = p->W, m2 = p->m2;
   const int KP = (W + 7) & ~7;
   const int nch = KP / 4;
   if ((W & 1) || 2 * m2 > 32 || nch > 34) return FNO_OK;   // not eligible: FP32 path only
-  std::vector<float> hi((size_t)4 * nch * 32, 0.0f), lo((size_t)4 * nch * 32, 0.0f);
+  std::vector<float> hi((size_t)4 * nch * 32, 0.0f), lo((size_t)4 * nch * 32, 0.0f), bf((size_t)4 * nch * 32, 0.0f);
   for (int q = 0; q < 2 * m2; ++q)
     for (int w = 0; w < W; ++w) {
       const int k2 = q < m2 ? q : q - m2;
       const float v = (float)(q < m2 ? cos2pi((long)k2 * w, W) : sin2pi((long)k2 * w, W));
       const size_t off = ((size_t)(q & 7) * 16 + (size_t)(q >> 3) * nch * 128 + (size_t)(w >> 2) * 128 + (w & 3) * 4) / 4;
       split_tf32_host(v, hi[off], lo[off]);
+      unsigned u;
+      std::memcpy(&u, &v, 4);
+      u = (u + 0x8000u) & 0xFFFF0000u;
+      std::memcpy(&bf[off], &u, 4);
     }
   int rc = upload(&p->tcF_hi, hi);
+  if (rc == FNO_OK) rc = upload(&p->tcF_bf, bf);
   if (rc != FNO_OK) return rc;
   rc = upload(&p->tcF_lo, lo);
   if (rc != FNO_OK) return rc;
@@ -141,6 +146,7 @@ void free_plan(Plan* p) {
   if (p->twX) cudaFree(p->twX);
   if (p->tcF_hi) cudaFree(p->tcF_hi);
   if (p->tcF_lo) cudaFree(p->tcF_lo);
+  if (p->tcF_bf) cudaFree(p->tcF_bf);
   cudaSetDevice(cur);
   cudaGetLastError();
   delete p;
@@ -213,7 +219,7 @@ int fno_sm_arch(void) { return 100; }
 const char* fno_last_error(void) { return t_err; }
 unsigned long long fno_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int fno_set_math_mode(int mode) {
-  if (mode != FNO_MATH_FP32 && mode != FNO_MATH_TF32) { set_error("fno_set_math_mode: unknown mode %d", mode); return FNO_E_ARG; }
+  if (mode != FNO_MATH_FP32 && mode != FNO_MATH_TF32 && mode != FNO_MATH_BF16) { set_error("fno_set_math_mode: unknown mode %d", mode); return FNO_E_ARG; }
   return g_math_mode.exchange(mode);
 }
 int fno_get_math_mode(void) { return g_math_mode.load(); }

@@ -34,6 +34,7 @@ struct Plan {
   // UMMA layout, tc_nch 16-byte w chunks per row (0 = path not available for this geometry)
   float* tcF_hi;
   float* tcF_lo;
+  float* tcF_bf;     // the same table rounded to bfloat16 (bf16 math mode)
   int tc_nch;
 };
 

@@ -85,6 +85,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
                    const float* __restrict__ b1, const float* __restrict__ W2, const float* __restrict__ stats,
                    float* __restrict__ dh, float* __restrict__ rec, BtGeo g, int C, int V, int tiles_per_sample,
                    int total_tiles, int single) {
+  FNO_SPLIT_CONSTS(single);                  // single: 0 = 3xTF32 (fp32 mode), 1 = tf32, 2 = bf16 operands
   extern __shared__ __align__(128) unsigned char bsm[];
   unsigned char* aw1_hi = bsm;
   unsigned char* aw1_lo = aw1_hi + AW1_BYTES;
@@ -133,8 +134,8 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
   for (int i = tid; i < BT_HID * BT_KC; i += BT_THREADS) {
     const int j = i / BT_KC, k = i - j * BT_KC;
     float hi = 0.f, lo = 0.f;
-    if (k < C) split_tf32(__ldg(W1 + (size_t)j * C + k), hi, lo);
-    else if (k == C) split_tf32(__ldg(b1 + j), hi, lo);
+    if (k < C) split_rm(__ldg(W1 + (size_t)j * C + k), hi, lo, sp_rnd, sp_msk);
+    else if (k == C) split_rm(__ldg(b1 + j), hi, lo, sp_rnd, sp_msk);
     const int off = (j & 7) * 16 + (j >> 3) * AW1_SBO + (k >> 2) * 128 + (k & 3) * 4;
     *reinterpret_cast<float*>(aw1_hi + off) = hi;
     *reinterpret_cast<float*>(aw1_lo + off) = lo;
@@ -285,7 +286,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
         if (VP > 1) { da = fmaf(w2r[1], go.y, da); aw2[1] = fmaf(gl, go.y, aw2[1]); }
         if (VP > 2) { da = fmaf(w2r[2], go.z, da); aw2[2] = fmaf(gl, go.z, aw2[2]); }
         if (VP > 3) { da = fmaf(w2r[3], go.w, da); aw2[3] = fmaf(gl, go.w, aw2[3]); }
-        split_tf32(da * gp, hi[p], lo[p]);
+        split_rm(da * gp, hi[p], lo[p], sp_rnd, sp_msk);
       }
       // dpre^T for (c) goes back into tensor memory, over the pre^T values this thread just read
       tmem_st16(tq, hi);
@@ -393,7 +394,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(chan(r, u, e), hi[u][e], lo[u][e]);
+        for (int e = 0; e < 4; ++e) split_rm(chan(r, u, e), hi[u][e], lo[u][e], sp_rnd, sp_msk);
       if (lw == 0) TRACE(16);
       mbar_wait(bh_free + s, phf);
       if (lw == 0) TRACE(17);
@@ -425,7 +426,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) split_tf32(chan(r, u, e), hi[u][e], lo[u][e]);
+        for (int e = 0; e < 4; ++e) split_rm(chan(r, u, e), hi[u][e], lo[u][e], sp_rnd, sp_msk);
       mbar_wait(d2_full + s, (((unsigned)it >> 1) & 1u) ^ 1u);
       if (lw == 0) TRACE(19);
 #pragma unroll
@@ -551,7 +552,7 @@ extern "C" int fno_head_bwd_tc(const float* h, const float* dout, const float* W
   }
   const int ctas = (int)(total < 148 ? total : 148);
   float* rec = static_cast<float*>(work);
-  const int single = g_math_mode.load() == FNO_MATH_TF32;
+  const int single = g_math_mode.load();
   if (V <= 2)
     head_bwd_tc_kernel<2><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
   else

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(TCF_THREADS, 1)
 head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
                    const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
                    float* __restrict__ out, HeadGeo g, int C, int V, int tiles_per_sample, int total_tiles, int single) {
+  FNO_SPLIT_CONSTS(single);                  // single: 0 = 3xTF32 (fp32 mode), 1 = tf32, 2 = bf16 operands
   extern __shared__ __align__(128) unsigned char tsm[];
   unsigned char* a_hi = tsm;                       // [2 stages][A_BYTES]
   unsigned char* a_lo = a_hi + 2 * A_BYTES;
@@ -90,7 +91,7 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
   for (int i = tid; i < TC_HID * TC_KP; i += TCF_THREADS) {
     const int n = i / TC_KP, k = i - n * TC_KP;
     float hi = 0.f, lo = 0.f;
-    if (k < C) split_tf32(__ldg(W1 + (size_t)n * C + k), hi, lo);
+    if (k < C) split_rm(__ldg(W1 + (size_t)n * C + k), hi, lo, sp_rnd, sp_msk);
     *reinterpret_cast<float*>(w_hi + b_off_bytes(n, k)) = hi;
     *reinterpret_cast<float*>(w_lo + b_off_bytes(n, k)) = lo;
   }
@@ -167,7 +168,7 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
         if (kc < 2 * ksteps) {
           float hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) split_tf32(raw[u][e], hi[e], lo[e]);
+          for (int e = 0; e < 4; ++e) split_rm(raw[u][e], hi[e], lo[e], sp_rnd, sp_msk);
           *reinterpret_cast<float4*>(a_hi + st * A_BYTES + abase + kc * 128) = make_float4(hi[0], hi[1], hi[2], hi[3]);
           if (!single) *reinterpret_cast<float4*>(a_lo + st * A_BYTES + abase + kc * 128) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
@@ -279,7 +280,7 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
     done.mark();
   }
   const int ctas = (int)(total < 148 ? total : 148);
-  const int single = g_math_mode.load() == FNO_MATH_TF32;
+  const int single = g_math_mode.load();
   if (V <= 2)
     head_fwd_tc_kernel<2><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
   else

@@ -320,7 +320,8 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
   const long t_begin = (p.total_tiles * (long)blockIdx.x) / (long)gridDim.x;          // total_tiles < 2^32, grid <= 148
   const long t_end = (p.total_tiles * (long)(blockIdx.x + 1)) / (long)gridDim.x;
   const int ntl = (int)(t_end - t_begin);
-  const int single = p.single;
+  const int single = p.single;                 // 0 = 3xTF32 (fp32 mode), 1 = tf32, 2 = bf16 operands
+  FNO_SPLIT_CONSTS(single);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -345,7 +346,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
       else if (k == C && p.bias != nullptr) v = __ldg(p.bias + n);
     }
     float hi, lo;
-    split_tf32(v, hi, lo);
+    split_rm(v, hi, lo, sp_rnd, sp_msk);
     const int off = (n >> 3) * KA * 8 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3);
     bW[off] = hi;
     bW[NPAD * KA + off] = lo;
@@ -386,7 +387,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
           for (int e = 0; e < 8; ++e) {
             const int k = 8 * g + e;
             const float v = (wv && k < m2x2) ? __ldg(p.twW + (size_t)k * p.WP + w + 2 * set) : 0.f;
-            split_tf32(v, hi[e], lo[e]);
+            split_rm(v, hi[e], lo[e], sp_rnd, sp_msk);
           }
           tmem_st8(ta + (set ? TM_F1 : 0u) + TM_FHI + 8u * g, hi);
           tmem_st8(ta + (set ? TM_F1 : 0u) + TM_FLO + 8u * g, lo);
@@ -463,7 +464,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
         if (KA - c0 >= 16) {
           float hi[16], lo[16];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) split_tf32(column(c0 + e), hi[e], lo[e]);
+          for (int e = 0; e < 16; ++e) split_rm(column(c0 + e), hi[e], lo[e], sp_rnd, sp_msk);
           if (!L2DBG(16)) {
             tmem_st16(ah + (unsigned)c0, hi);
             if (!single) tmem_st16(al + (unsigned)c0, lo);
@@ -471,7 +472,7 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
         } else {
           float hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) split_tf32(column(c0 + e), hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) split_rm(column(c0 + e), hi[e], lo[e], sp_rnd, sp_msk);
           if (!L2DBG(16)) {
             tmem_st8(ah + (unsigned)c0, hi);
             if (!single) tmem_st8(al + (unsigned)c0, lo);
@@ -664,8 +665,8 @@ layer2d_tc_kernel(const L2Args p, const __grid_constant__ CUtensorMap tm_a, cons
       for (int i = 0; i < NFB; ++i) {
         if (lane + 32 * i < tile_f4) {
           float4 hi, lo;
-          split_tf32(raw[i].x, hi.x, lo.x); split_tf32(raw[i].y, hi.y, lo.y);
-          split_tf32(raw[i].z, hi.z, lo.z); split_tf32(raw[i].w, hi.w, lo.w);
+          split_rm(raw[i].x, hi.x, lo.x, sp_rnd, sp_msk); split_rm(raw[i].y, hi.y, lo.y, sp_rnd, sp_msk);
+          split_rm(raw[i].z, hi.z, lo.z, sp_rnd, sp_msk); split_rm(raw[i].w, hi.w, lo.w, sp_rnd, sp_msk);
           dh[32 * i] = hi;
           dl[32 * i] = lo;
         }
@@ -942,7 +943,7 @@ int launch_layer2d_tc(const Plan* p, const float* Y, const float* a, const float
   args.twW = p->twW; args.WP = p->WP; args.W = p->W; args.m2 = p->m2; args.KQ = KQ; args.C = C;
   args.RS = p->D1 * p->H; args.tile_floats = tile_floats; args.total_tiles = total;
   args.transpose_w = transpose_w; args.apply_gelu = apply_gelu;
-  args.single = g_math_mode.load() == FNO_MATH_TF32;
+  args.single = g_math_mode.load();
   args.rs_div.init((unsigned)args.RS);
   args.trace = nullptr;
   args.dbg = 0;

@@ -156,5 +156,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// The same split with the rounding position as run-time values (kernel-uniform, so they cost registers, not
+// instructions): (0x1000, 0xffffe000) = tf32 (fp32 and tf32 modes), (0x8000, 0xffff0000) = bfloat16 (bf16 mode: every MMA
+// operand is a bf16-representable value, one kind::tf32 pass, fp32 accumulation = the arithmetic of a bf16 tensor-core MMA).
+__device__ __forceinline__ void split_rm(float x, float& hi, float& lo, unsigned rnd, unsigned msk) {
+  hi = __uint_as_float((__float_as_uint(x) + rnd) & msk);
+  lo = x - hi;
+}
+#define FNO_SPLIT_CONSTS(mode) \
+  const unsigned sp_rnd = (mode) == 2 ? 0x8000u : 0x1000u, sp_msk = (mode) == 2 ? 0xffff0000u : 0xffffe000u
+
 }  // namespace
 }  // namespace fno

@@ -46,6 +46,7 @@ constexpr unsigned TA_TM_COLS = 512;
 __global__ void __launch_bounds__(TA_THREADS, 1)
 fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const float* __restrict__ Fhi,
                  const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles, int single) {
+  FNO_SPLIT_CONSTS(single);                  // single: 0 = 3xTF32 (fp32 mode), 1 = tf32, 2 = bf16 operands
   extern __shared__ __align__(128) unsigned char wsm[];
   const int raw_bytes = TW_M * W * 4;                 // one tile of rows (multiple of 512)
   const int f_bytes = 4 * nch * 128;
@@ -124,8 +125,8 @@ fwd2d_tca_kernel(const float* __restrict__ x, float* __restrict__ T1, const floa
           const int w = 8 * ks + e;                            // W is even: pairs are all-in or all-out
           float2 v = make_float2(0.f, 0.f);
           if (live && w < W) v = *reinterpret_cast<const float2*>(rp + w);
-          split_tf32(v.x, hi[e], lo[e]);
-          split_tf32(v.y, hi[e + 1], lo[e + 1]);
+          split_rm(v.x, hi[e], lo[e], sp_rnd, sp_msk);
+          split_rm(v.y, hi[e + 1], lo[e + 1], sp_rnd, sp_msk);
         }
         tmem_st8(ta + (unsigned)(8 * ks), hi);
         if (!single) tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1)
 fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact, float* __restrict__ ds_out,
                   float* __restrict__ T1, const float* __restrict__ Fhi,
                  const float* __restrict__ Flo, long R, int W, int nch, int TQ, int total_tiles, int single) {
+  FNO_SPLIT_CONSTS(single);                  // single: 0 = 3xTF32 (fp32 mode), 1 = tf32, 2 = bf16 operands
   extern __shared__ __align__(128) unsigned char wsm[];
   constexpr int HR = TW_M / 2;                        // rows per half-tile slot
   const int slot_bytes = HR * W * 4;                  // multiple of 256
@@ -315,8 +317,8 @@ fwd2d_tcap_kernel(const float* __restrict__ x, const float* __restrict__ preact,
             v = make_float2(gv.x * gelu_fast_grad(sv.x), gv.y * gelu_fast_grad(sv.y));
             *reinterpret_cast<float2*>(rp + w) = v;            // dS, bulk-stored by the producer warp
           }
-          split_tf32(v.x, hi[e], lo[e]);
-          split_tf32(v.y, hi[e + 1], lo[e + 1]);
+          split_rm(v.x, hi[e], lo[e], sp_rnd, sp_msk);
+          split_rm(v.y, hi[e + 1], lo[e + 1], sp_rnd, sp_msk);
         }
         tmem_st8(ta + (unsigned)(8 * ks), hi);
         if (!single) tmem_st8(ta + TA_TM_LO + (unsigned)(8 * ks), lo);
@@ -405,8 +407,8 @@ int launch_fwd2d_tca(const Plan* p, const float* x, float* T1, long planes, cuda
     return 1;
   const int ctas = (int)(tiles < 148 ? tiles : 148);
   const int TQ = (2 * p->m2 + 3) & ~3;
-  fwd2d_tca_kernel<<<ctas, TA_THREADS, smem, st>>>(x, T1, p->tcF_hi, p->tcF_lo, R, p->W, p->tc_nch, TQ, (int)tiles,
-                                                   g_math_mode.load() == FNO_MATH_TF32);
+  fwd2d_tca_kernel<<<ctas, TA_THREADS, smem, st>>>(x, T1, (g_math_mode.load() == FNO_MATH_BF16 ? p->tcF_bf : p->tcF_hi), p->tcF_lo, R, p->W, p->tc_nch, TQ, (int)tiles,
+                                                   g_math_mode.load());
   count_launch();
   return check_launch("fwd2d_tca_kernel");
 }
@@ -429,8 +431,8 @@ int launch_fwd2d_tcap(const Plan* p, const float* g, const float* preact, float*
     return 1;
   const int ctas = (int)(tiles < 148 ? tiles : 148);
   const int TQ = (2 * p->m2 + 3) & ~3;
-  fwd2d_tcap_kernel<<<ctas, TA_THREADS, smem, st>>>(g, preact, ds_out, T1, p->tcF_hi, p->tcF_lo, R, p->W, p->tc_nch, TQ,
-                                                    (int)tiles, g_math_mode.load() == FNO_MATH_TF32);
+  fwd2d_tcap_kernel<<<ctas, TA_THREADS, smem, st>>>(g, preact, ds_out, T1, (g_math_mode.load() == FNO_MATH_BF16 ? p->tcF_bf : p->tcF_hi), p->tcF_lo, R, p->W, p->tc_nch, TQ,
+                                                    (int)tiles, g_math_mode.load());
   count_launch();
   return check_launch("fwd2d_tcap_kernel");
 }

@@ -537,12 +537,13 @@ def lift_bwd(geo: TrunkGeo, x, grid, stats, dh, W0_shape):
     return gW0, gb0
 
 
-MATH_MODES = {"fp32": 0, "tf32": 1}
+MATH_MODES = {"fp32": 0, "tf32": 1, "bf16": 2}
 
 
 def set_math_mode(mode: str) -> str:
-    """Arithmetic mode of the tensor-core kernels: "fp32" (3xTF32 split, <= 1e-5 relative; default) or
-    "tf32" (single kind::tf32 pass, stated bound <= 2e-3 relative).  Returns the previous mode."""
+    """Arithmetic mode of the tensor-core kernels: "fp32" (3xTF32 split, <= 1e-5 relative; default), "tf32" (single
+    kind::tf32 pass, stated bound <= 2e-3 relative) or "bf16" (operands rounded to bfloat16, single pass, fp32 accumulate,
+    stated bound <= 2e-2).  Returns the previous mode."""
     if mode not in MATH_MODES:
         raise FnoError(f"unknown math mode {mode!r} (expected one of {sorted(MATH_MODES)})")
     prev = load().fno_set_math_mode(MATH_MODES[mode])

@@ -480,10 +480,15 @@ def test_fwd_transform_tensor_core_path_with_gelu_grad(lib, monkeypatch, B, C, H
 # relative (max |err| / max |ref|) on outputs and gradients; fp32 mode stays <= 1e-5.
 # ---------------------------------------------------------------------------------------------
 TF32_TOL = 2e-3
+# bf16 math mode: every MMA operand rounded to bfloat16 (8-bit significand), one pass, fp32 accumulation.  Stated bound
+# <= 2e-2 relative (max-norm); measured 2e-3 .. 6e-3.
+BF16_TOL = 2e-2
+MODE_TOL = {"tf32": TF32_TOL, "bf16": BF16_TOL}
 
 
+@pytest.mark.parametrize("low", ["tf32", "bf16"])
 @pytest.mark.parametrize("spatial,C,V,B", [((64, 64), 20, 2, 3), ((40, 50), 23, 4, 2)])
-def test_head_tf32_mode(lib, spatial, C, V, B):
+def test_head_tf32_mode(lib, spatial, C, V, B, low):
     from fno_b200 import ops
     from oracle import fno_port as P
 
@@ -505,7 +510,7 @@ def test_head_tf32_mode(lib, spatial, C, V, B):
     gout = torch.randn(out_ref.shape, generator=g, dtype=torch.float64)
     out_ref.backward(gout)
     errs = {}
-    for mode in ("tf32", "fp32"):
+    for mode in (low, "fp32"):
         prev = lib.set_math_mode(mode)
         try:
             assert lib.get_math_mode() == mode
@@ -523,10 +528,10 @@ def test_head_tf32_mode(lib, spatial, C, V, B):
         errs[mode] = e
     assert lib.get_math_mode() == "fp32"
     assert max(errs["fp32"].values()) < TOL, errs["fp32"]
-    assert max(errs["tf32"].values()) < TF32_TOL, errs["tf32"]
-    # the mode switch is real: single-pass TF32 is visibly less accurate than the 3xTF32 split
-    assert errs["tf32"]["out"] > 10 * errs["fp32"]["out"], errs
-    print("head tf32-mode errors:", {k: f"{v:.2e}" for k, v in errs["tf32"].items()})
+    assert max(errs[low].values()) < MODE_TOL[low], errs[low]
+    # the mode switch is real: a single reduced-precision pass is visibly less accurate than the 3xTF32 split
+    assert errs[low]["out"] > 10 * errs["fp32"]["out"], errs
+    print(f"head {low}-mode errors:", {k: f"{v:.2e}" for k, v in errs[low].items()})
 
 
 # ---------------------------------------------------------------------------------------------
@@ -550,9 +555,10 @@ def test_device_windows_match_host_windows(lib, spatial, T, V, T0, R):
     assert sorted(seen.tolist()) == list(range(len(ds)))
 
 
-def test_fwd_transform_tf32_mode(lib, monkeypatch):
-    """tf32 math mode on the K1 tensor-core kernels (plain and GELU'-premultiply forms): single kind::tf32 pass,
-    stated bound <= 2e-3 relative; fp32 mode (3xTF32) <= 1e-5 on the same inputs."""
+@pytest.mark.parametrize("low", ["tf32", "bf16"])
+def test_fwd_transform_tf32_mode(lib, monkeypatch, low):
+    """tf32 / bf16 math modes on the K1 tensor-core kernels (plain and GELU'-premultiply forms): single pass, stated
+    bound <= 2e-3 (tf32) / 2e-2 (bf16) relative; fp32 mode (3xTF32) <= 1e-5 on the same inputs."""
     monkeypatch.setattr(lib, "K1_TENSOR_CORES", True)
     B, C, H, W, m1, m2 = 4, 20, 130, 130, 12, 12
     rng = np.random.default_rng(5)
@@ -563,7 +569,7 @@ def test_fwd_transform_tf32_mode(lib, monkeypatch):
     ds_ref = g.astype(np.float64) * O.gelu_grad(s_.astype(np.float64))
     ref_pre = O.fwd_transform(ds_ref, (m1, m2), cmode=1, scale=1.0 / (H * W))
     errs = {}
-    for mode in ("tf32", "fp32"):
+    for mode in (low, "fp32"):
         prev = lib.set_math_mode(mode)
         try:
             X = lib.fwd_transform(plan, dev(g), cmode=0, scale=1.0).cpu().numpy()
@@ -573,10 +579,47 @@ def test_fwd_transform_tf32_mode(lib, monkeypatch):
             lib.set_math_mode(prev)
         errs[mode] = (O.rel_err(X, ref_plain), O.rel_err(Xp, ref_pre), O.rel_err(ds.cpu().numpy(), ds_ref))
     assert max(errs["fp32"]) < TOL, errs
-    assert max(errs["tf32"][:2]) < TF32_TOL, errs
-    assert errs["tf32"][2] < TOL                    # dS itself is computed in fp32 in both modes
-    assert errs["tf32"][0] > 10 * errs["fp32"][0], errs
-    print("K1 tf32-mode errors (plain, premultiply):", f"{errs['tf32'][0]:.2e}", f"{errs['tf32'][1]:.2e}")
+    assert max(errs[low][:2]) < MODE_TOL[low], errs
+    assert errs[low][2] < TOL                       # dS itself is computed in fp32 in every mode
+    assert errs[low][0] > 10 * errs["fp32"][0], errs
+    if low == "bf16":
+        assert errs[low][0] > 2 * 3.5e-4, errs       # ... and bf16 is visibly coarser than tf32 (measured 2.9e-4)
+    print(f"K1 {low}-mode errors (plain, premultiply):", f"{errs[low][0]:.2e}", f"{errs[low][1]:.2e}")
+
+
+@pytest.mark.parametrize("low", ["tf32", "bf16"])
+def test_fourier_layer_reduced_precision_modes(lib, low):
+    """One whole Fourier layer (K1 -> K2 -> fused tcgen05 K3 + bypass + GELU, forward and backward) in tf32 / bf16 mode
+    against the fp64 oracle: stated bounds 2e-3 / 2e-2; fp32 mode <= 1e-5 on the same inputs."""
+    from fno_b200 import ops
+
+    B, C, n, m = 2, 20, 66, 12
+    rng = np.random.default_rng(21)
+    a = rng.standard_normal((B, C, n, n)).astype(np.float32)
+    wl = (rng.standard_normal((C, C, 1, 1)) / C ** 0.5).astype(np.float32)
+    bl = rng.standard_normal(C).astype(np.float32)
+    ws = [((rng.random((C, C, m, m)) + 1j * rng.random((C, C, m, m))) / C).astype(np.complex64) for _ in range(2)]
+    g = rng.standard_normal((B, C, n, n)).astype(np.float32)
+    ref, _ = O.fourier_layer_forward(a, ws, wl, bl, True)
+    gref = O.fourier_layer_backward(a, ws, wl, bl, True, g)
+    errs = {}
+    for mode in (low, "fp32"):
+        prev = lib.set_math_mode(mode)
+        try:
+            ad = dev(a).requires_grad_()
+            wld, bld = dev(wl).requires_grad_(), dev(bl).requires_grad_()
+            wsd = [dev(w).requires_grad_() for w in ws]
+            out = ops.fourier_layer(ad, wld, bld, True, wsd)
+            out.backward(dev(g))
+            torch.cuda.synchronize()
+        finally:
+            lib.set_math_mode(prev)
+        errs[mode] = (O.rel_err(out.detach().cpu().numpy(), ref), O.rel_err(ad.grad.cpu().numpy(), gref[0]),
+                      O.rel_err(wsd[0].grad.cpu().numpy(), gref[1][0]))
+    assert max(errs["fp32"]) < TOL, errs
+    assert max(errs[low]) < MODE_TOL[low], errs
+    assert errs[low][0] > 10 * errs["fp32"][0], errs
+    print(f"Fourier layer {low}-mode errors (out, d input, d spectral weight):", [f"{e:.2e}" for e in errs[low]])
 
 
 def test_new_entry_points_reject_bad_arguments(lib):
