@@ -38,7 +38,7 @@ constexpr int BT_PX = 64;            // pixels per tile
 constexpr int BT_HID = 128;
 constexpr int BT_KC = 24;            // padded channels: K of (a), N of (b); C + 1 <= 24
 constexpr int BT_NC = 32;            // N of (c)  (M = 128 needs N % 16 == 0)
-constexpr int BT_GV = 4;             // floats per pixel in the staged dout tile
+constexpr int BT_GV = 8;             // floats per pixel of a staged dout tile / per-variable record stride (V <= 8)
 constexpr int BT_EPI_WARPS = 16;
 constexpr int BT_LD_WARPS = 6;
 constexpr int BT_MMA_WARP = BT_EPI_WARPS;
@@ -275,17 +275,24 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       float pre[16];
       tmem_ld16(tq, pre);
       float hi[16], lo[16];
-      const float4* __restrict__ gq = gt + s * BT_PX + 16 * colq;
+      const float4* __restrict__ gq = gt + (s * BT_PX + 16 * colq) * 2;
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         float gl, gp;
         gelu_fast_both(pre[p], gl, gp);
-        const float4 go = gq[p];                        // dout * std of this pixel (warp-wide broadcast)
+        const float4 go = gq[2 * p];                    // dout * std of this pixel (warp-wide broadcast)
         float da = w2r[0] * go.x;
         aw2[0] = fmaf(gl, go.x, aw2[0]);
         if (VP > 1) { da = fmaf(w2r[1], go.y, da); aw2[1] = fmaf(gl, go.y, aw2[1]); }
         if (VP > 2) { da = fmaf(w2r[2], go.z, da); aw2[2] = fmaf(gl, go.z, aw2[2]); }
         if (VP > 3) { da = fmaf(w2r[3], go.w, da); aw2[3] = fmaf(gl, go.w, aw2[3]); }
+        if (VP > 4) {
+          const float4 g2 = gq[2 * p + 1];
+          da = fmaf(w2r[4], g2.x, da); aw2[4] = fmaf(gl, g2.x, aw2[4]);
+          if (VP > 5) { da = fmaf(w2r[5], g2.y, da); aw2[5] = fmaf(gl, g2.y, aw2[5]); }
+          if (VP > 6) { da = fmaf(w2r[6], g2.z, da); aw2[6] = fmaf(gl, g2.z, aw2[6]); }
+          if (VP > 7) { da = fmaf(w2r[7], g2.w, da); aw2[7] = fmaf(gl, g2.w, aw2[7]); }
+        }
         split_rm(da * gp, hi[p], lo[p], sp_rnd, sp_msk);
       }
       // dpre^T for (c) goes back into tensor memory, over the pre^T values this thread just read
@@ -340,8 +347,11 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
     const int kq = lt >> 6;                        // stages the 4-channel chunks kq and kq + 3
     const int npix = (int)g.npix;
     const size_t sample_stride = (size_t)C * g.plane;
-    float gb2[BT_GV] = {0.f, 0.f, 0.f, 0.f};
-    struct Raw { float x[2][4]; float go[BT_GV]; float sd[BT_GV]; bool valid; };
+    constexpr int GV = VP > 4 ? 8 : 4;           // variables carried by this instantiation's loaders
+    float gb2[GV];
+#pragma unroll
+    for (int v = 0; v < GV; ++v) gb2[v] = 0.f;
+    struct Raw { float x[2][4]; float go[GV]; float sd[GV]; bool valid; };
     // Loads only: nothing in load_raw may USE a loaded value (the warp would sit out the whole DRAM latency
     // there); masking and the dout * std product happen one iteration later, at staging time.  Every load is
     // executed, from a clamped in-range address (no branches, no per-element 64-bit address rebuilds).
@@ -374,7 +384,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
         const float* __restrict__ sd = stats + (size_t)b * 2 * V + V;
         const float* __restrict__ op = dout + ((size_t)b * npix + p) * V;
 #pragma unroll
-        for (int v = 0; v < BT_GV; ++v) {
+        for (int v = 0; v < GV; ++v) {
           const int vc = v < V ? v : V - 1;
           r.go[v] = __ldg(op + vc);
           r.sd[v] = __ldg(sd + vc);
@@ -406,13 +416,14 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
       }
       if (kq == 0) {
         mbar_wait(g_free + s, phf);
-        float go[BT_GV];
+        float go[GV];
 #pragma unroll
-        for (int v = 0; v < BT_GV; ++v) {
+        for (int v = 0; v < GV; ++v) {
           go[v] = (r.valid && v < V) ? r.go[v] * r.sd[v] : 0.f;
           gb2[v] += go[v];
         }
-        gt[s * BT_PX + px] = make_float4(go[0], go[1], go[2], go[3]);
+        gt[(s * BT_PX + px) * 2] = make_float4(go[0], go[1], go[2], go[3]);
+        if (GV > 4) gt[(s * BT_PX + px) * 2 + 1] = make_float4(go[GV - 4], go[GV - 3], go[GV - 2], go[GV - 1]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -465,7 +476,7 @@ head_bwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ dout, 
     if (kq == 0) {                                  // gb2: the two dout-staging warps reduce over their 32 pixels each
 #pragma unroll
       for (int v = 0; v < BT_GV; ++v) {
-        float t = gb2[v];
+        float t = v < GV ? gb2[v < GV ? v : 0] : 0.f;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
         if (lane == 0) myrec[REC_B2 + lw * BT_GV + v] = t;
@@ -546,7 +557,8 @@ extern "C" int fno_head_bwd_tc(const float* h, const float* dout, const float* W
   static PerDeviceOnce done;
   if (done.need()) {
     if (cudaFuncSetAttribute(head_bwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(head_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess)
+        cudaFuncSetAttribute(head_bwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(head_bwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, BT_SMEM) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_bwd_tc)");
     done.mark();
   }
@@ -555,8 +567,10 @@ extern "C" int fno_head_bwd_tc(const float* h, const float* dout, const float* W
   const int single = g_math_mode.load();
   if (V <= 2)
     head_bwd_tc_kernel<2><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
-  else
+  else if (V <= 4)
     head_bwd_tc_kernel<4><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
+  else
+    head_bwd_tc_kernel<8><<<ctas, BT_THREADS, BT_SMEM, st>>>(h, dout, W1, b1, W2, stats, dh, rec, g, C, V, (int)tps, (int)total, single);
   count_launch();
   rc = check_launch("head_bwd_tc_kernel");
   if (rc != FNO_OK) return rc;

@@ -29,7 +29,7 @@ namespace {
 constexpr int TC_M = 128;          // pixels per tile = TMEM lanes
 constexpr int TC_HID = 128;        // hidden units = accumulator columns
 constexpr int TC_KP = 32;          // channel padding of the staged operands (4 core-matrix groups of 8)
-constexpr int TC_VP = 4;
+constexpr int TC_VP = 8;           // output variables: shared-memory rows are padded to 4 (NV <= 4) or 8 floats
 
 struct HeadGeo {
   int R_in, W_in, R_out, Wp;
@@ -67,6 +67,7 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
   unsigned char* w_hi = a_lo + 2 * A_BYTES;        // B_BYTES
   unsigned char* w_lo = w_hi + B_BYTES;
   float* W2s = reinterpret_cast<float*>(w_lo + B_BYTES);   // [HID][VP]
+  constexpr int VPAD = NV > 4 ? 8 : 4;                     // floats per W2 / output row of this instantiation
   float* b1s = W2s + TC_HID * TC_VP;                       // [HID]
   float* ox = b1s + TC_HID;                                // [2 tiles][4 quarters][TC_M][VP] partial outputs
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(ox + 2 * 4 * TC_M * TC_VP);
@@ -95,8 +96,8 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
     *reinterpret_cast<float*>(w_hi + b_off_bytes(n, k)) = hi;
     *reinterpret_cast<float*>(w_lo + b_off_bytes(n, k)) = lo;
   }
-  for (int i = tid; i < TC_HID * TC_VP; i += TCF_THREADS) {
-    const int j = i / TC_VP, v = i - j * TC_VP;
+  for (int i = tid; i < TC_HID * VPAD; i += TCF_THREADS) {
+    const int j = i / VPAD, v = i - j * VPAD;
     W2s[i] = (v < V) ? __ldg(W2 + (size_t)v * TC_HID + j) : 0.f;
   }
   for (int i = tid; i < TC_HID; i += TCF_THREADS) b1s[i] = __ldg(b1 + i);
@@ -195,7 +196,9 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
       // -- epilogue of tile it: bias, GELU, 128 -> V product on this thread's pixel and column quarter
       mbar_wait(d_full + st, ph);
       tc_fence_after();
-      float o[TC_VP] = {0.f, 0.f, 0.f, 0.f};
+      float o[VPAD];
+#pragma unroll
+      for (int v = 0; v < VPAD; ++v) o[v] = 0.f;
       {
         float v[32];
         const int j0 = colq * 32;
@@ -207,35 +210,43 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
         for (int i = 0; i < 32; ++i) {
           const float gl = gelu_fast(v[i] + b1s[j0 + i]);
           if (NV == 2) {
-            const float2 w = *reinterpret_cast<const float2*>(W2s + (j0 + i) * TC_VP);
+            const float2 w = *reinterpret_cast<const float2*>(W2s + (j0 + i) * VPAD);
             o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
           } else {
-            const float4 w = *reinterpret_cast<const float4*>(W2s + (j0 + i) * TC_VP);
-            o[0] = fmaf(w.x, gl, o[0]); o[1] = fmaf(w.y, gl, o[1]);
-            o[2] = fmaf(w.z, gl, o[2]); o[3] = fmaf(w.w, gl, o[3]);
+#pragma unroll
+            for (int q = 0; q < VPAD / 4; ++q) {
+              const float4 w = *reinterpret_cast<const float4*>(W2s + (j0 + i) * VPAD + 4 * q);
+              o[4 * q + 0] = fmaf(w.x, gl, o[4 * q + 0]); o[4 * q + 1] = fmaf(w.y, gl, o[4 * q + 1]);
+              o[4 * q + 2] = fmaf(w.z, gl, o[4 * q + 2]); o[4 * q + 3] = fmaf(w.w, gl, o[4 * q + 3]);
+            }
           }
         }
       }
       // combine the four column quarters through shared memory (double-buffered: one barrier per
       // tile); the quarter that finishes the tile rotates so the extra work is spread over all warps
       float* oxb = ox + (size_t)(it & 1) * 4 * TC_M * TC_VP;
-      *reinterpret_cast<float4*>(oxb + (colq * TC_M + m) * TC_VP) = make_float4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+      for (int q = 0; q < VPAD / 4; ++q)
+        *reinterpret_cast<float4*>(oxb + (colq * TC_M + m) * VPAD + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       named_bar_sync(1, TCF_EPI_THREADS);
       if (colq == (it & 3)) {
-        float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float of[VPAD];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 u = *reinterpret_cast<const float4*>(oxb + (q * TC_M + m) * TC_VP);
-          acc4.x += u.x; acc4.y += u.y; acc4.z += u.z; acc4.w += u.w;
-        }
-        const float of[TC_VP] = {acc4.x, acc4.y, acc4.z, acc4.w};
+        for (int v = 0; v < VPAD; ++v) of[v] = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int r = 0; r < VPAD / 4; ++r) {
+            const float4 u = *reinterpret_cast<const float4*>(oxb + (q * TC_M + m) * VPAD + 4 * r);
+            of[4 * r] += u.x; of[4 * r + 1] += u.y; of[4 * r + 2] += u.z; of[4 * r + 3] += u.w;
+          }
         const long p = p0 + m;
         if (p < g.npix) {
           const float* __restrict__ mean = stats + (size_t)b * 2 * V;
           const float* __restrict__ sd = mean + V;
           float* __restrict__ op = out + ((size_t)b * g.npix + p) * V;
 #pragma unroll
-          for (int v = 0; v < TC_VP; ++v)
+          for (int v = 0; v < VPAD; ++v)
             if (v < V) op[v] = fmaf(of[v] + __ldg(b2 + v), __ldg(sd + v), __ldg(mean + v));
         }
       }
@@ -275,7 +286,8 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
   static PerDeviceOnce done;
   if (done.need()) {
     if (cudaFuncSetAttribute(head_fwd_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        cudaFuncSetAttribute(head_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        cudaFuncSetAttribute(head_fwd_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(head_fwd_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(head_fwd_tc)");
     done.mark();
   }
@@ -283,8 +295,10 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
   const int single = g_math_mode.load();
   if (V <= 2)
     head_fwd_tc_kernel<2><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
-  else
+  else if (V <= 4)
     head_fwd_tc_kernel<4><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
+  else
+    head_fwd_tc_kernel<8><<<ctas, TCF_THREADS, smem, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total, single);
   count_launch();
   return check_launch("head_fwd_tc_kernel");
 }

@@ -565,7 +565,7 @@ def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
     if tuple(h.shape[2:]) != geo.padded or W1.shape[1] != C or W2.shape[1] != HID:
         raise FnoError(f"head: inconsistent shapes h {tuple(h.shape)}, fc1 {tuple(W1.shape)}, fc2 {tuple(W2.shape)}")
     out = torch.empty((B,) + geo.spatial + (V,), dtype=torch.float32, device=h.device)
-    if HEAD_TC and HID == 128 and C <= 32 and V <= 4:
+    if HEAD_TC and HID == 128 and C <= 32 and V <= 8:
         # tensor-core path (tcgen05 kind::tf32, 3xTF32 split: fp32-mode accuracy)
         _check(load().fno_head_fwd_tc(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                       stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
@@ -585,7 +585,7 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
     dh = torch.empty_like(h)
     gW1, gb1 = torch.empty_like(W1), torch.empty(HID, dtype=torch.float32, device=h.device)
     gW2, gb2 = torch.empty_like(W2), torch.empty(V, dtype=torch.float32, device=h.device)
-    tc = HEAD_BWD_TC and HID == 128 and C <= 23 and V <= 4
+    tc = HEAD_BWD_TC and HID == 128 and C <= 23 and V <= 8
     fn = lib.fno_head_bwd_tc if tc else lib.fno_head_bwd      # tcgen05 3xTF32 path / FP32 CUDA-core path
     _check(fn(h.data_ptr(), dout.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
               stats.data_ptr(), dh.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(),

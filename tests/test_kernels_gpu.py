@@ -384,6 +384,9 @@ HEAD_CASES = [
     ((64, 64), 20, 2, 5),       # 320 64-pixel tiles: several pipelined tiles per persistent CTA (tensor-core backward)
     ((40, 50), 23, 4, 3),       # widest tensor-core case (C + bias column = 24), ragged last tile, V = 4
     ((128, 128), 20, 2, 2),     # cfg-1 plane
+    ((16, 16, 22), 20, 5, 2),   # cfg-4 shape class: 5 variables (tensor-core heads with 8-wide variable rows), many tiles
+    ((30, 34), 12, 8, 2),       # V = 8: the widest tensor-core case
+    ((20, 20), 8, 7, 1),
 ]
 
 
@@ -391,7 +394,7 @@ HEAD_CASES = [
 @pytest.mark.parametrize("spatial,C,V,B", HEAD_CASES)
 def test_head_forward_backward(lib, monkeypatch, spatial, C, V, B, bwd_tc):
     monkeypatch.setattr(lib, "HEAD_BWD_TC", bwd_tc)
-    if bwd_tc and (C > 23 or V > 4):
+    if bwd_tc and (C > 23 or V > 8):
         pytest.skip("outside the tensor-core backward's envelope (FP32 path covers it)")
     from fno_b200 import ops
     from oracle import fno_port as P
