@@ -110,6 +110,10 @@ int fno_mix_fwd(const fno_plan* plan, const float* X, const float* const* w, flo
  * gX or gw may be NULL to skip that half.                                                      */
 int fno_mix_bwd(const fno_plan* plan, const float* X, const float* gY, const float* const* w,
                 float* gX, float* const* gw, int B, int Ci, int Co, fno_stream_t stream);
+/* 1 if fno_mix_fwd / fno_mix_bwd run this shape on the tensor cores (tcgen05, 3xTF32 in fp32 mode):
+ * 32 < max(Ci, Co) <= 64 and an even innermost mode count (BASELINE configs[2], width 64); the
+ * entry points fall back to the FP32 kernels for tensors that are not 16-byte aligned.        */
+int fno_mix_tc_supported(const fno_plan* plan, int Ci, int Co);
 
 /* ---- K3: zero-padding inverse transform with fused epilogue --------------------------------- */
 /* Replaces torch.zeros + slice-assign + torch.fft.irfft2 (fno/fno.py:76-92) and, when `addend`

@@ -339,6 +339,11 @@ int fno_layer2d_inv_fused(const fno_plan* plan, const float* Y, const float* a, 
                            transpose_w, static_cast<cudaStream_t>(stream));
 }
 
+int fno_mix_tc_supported(const fno_plan* plan, int Ci, int Co) {
+  const Plan* p = P(plan);
+  return (p != nullptr && Ci > 0 && Co > 0 && mix_tc_supported(p, Ci, Co)) ? 1 : 0;
+}
+
 int fno_mix_fwd(const fno_plan* plan, const float* X, const float* const* w, float* Y, int B, int Ci, int Co,
                 fno_stream_t stream) {
   const Plan* p = P(plan);

@@ -81,6 +81,7 @@ int launch_mix_bwd_data(const Plan* p, const float* gY, const float* const* w, f
                         int Ci, int Co, cudaStream_t st);
 int launch_mix_bwd_weight(const Plan* p, const float* X, const float* gY, float* const* gw, int B,
                           int Ci, int Co, cudaStream_t st);
+bool mix_tc_supported(const Plan* p, int Ci, int Co);
 
 // ---- device helpers --------------------------------------------------------------------------
 // exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery): 4 instructions instead

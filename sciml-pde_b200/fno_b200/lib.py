@@ -71,6 +71,7 @@ def load():
             "fno_sc3d_fwd_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, vp]),
             "fno_mix_fwd": (i, [vp, vp, vpp, vp, i, i, i, vp]),
             "fno_mix_bwd": (i, [vp, vp, vp, vpp, vp, vpp, i, i, i, vp]),
+            "fno_mix_tc_supported": (i, [vp, i, i]),
             "fno_sc2d_inv_transform": (i, [vp, vp, vp, vp, vp, l, i, f, i, vp]),
             "fno_sc3d_inv_transform": (i, [vp, vp, vp, vp, vp, vp, l, i, f, i, vp]),
             "fno_layer2d_fused_supported": (i, [vp, i]),
@@ -114,7 +115,7 @@ EXPORTED_SYMBOLS = (
     "fno_set_math_mode", "fno_get_math_mode", "fno_window_gather",
     "fno_plan2d_create", "fno_plan3d_create", "fno_plan_destroy", "fno_plan_workspace_bytes",
     "fno_sc2d_fwd_transform", "fno_sc2d_fwd_workspace_bytes", "fno_sc2d_fwd_transform_ws",
-    "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd",
+    "fno_sc3d_fwd_transform", "fno_mix_fwd", "fno_mix_bwd", "fno_mix_tc_supported",
     "fno_sc2d_inv_transform", "fno_sc3d_inv_transform", "fno_layer2d_fused_supported",
     "fno_layer2d_fused_workspace_bytes", "fno_layer2d_inv_fused", "fno_pointwise_fwd",
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad", "fno_pointwise_bwd",
@@ -368,6 +369,11 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
     for k, t in enumerate(tensors):
         arr[k] = t.data_ptr()
     return arr
+
+
+def mix_tc_supported(plan: Plan, Ci: int, Co: int) -> bool:
+    """True when K2 (mix_fwd / mix_bwd) runs this shape on the tensor cores (width 33..64, even innermost mode count)."""
+    return bool(load().fno_mix_tc_supported(plan.handle, int(Ci), int(Co)))
 
 
 @_on_tensor_device

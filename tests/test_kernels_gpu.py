@@ -215,6 +215,68 @@ def test_mix_fwd_bwd(lib, B, Ci, Co, spatial, modes):
         assert O.rel_err(got.cpu().numpy(), ref) < TOL
 
 
+# K2 on the tensor cores (mix_tc_kernel / mix_wgrad_tc_kernel): width 33..64 with an even innermost mode count.
+# BASELINE configs[2] shape first; then ragged batches (one chunk of 32 partly filled, several chunks), channel counts
+# that are not multiples of 8, Ci != Co, a 3-D spectrum, and shapes just outside the envelope (FP32 kernels).
+@pytest.mark.parametrize("B,Ci,Co,spatial,modes,tc", [
+    (32, 64, 64, (66, 66), (16, 16), True),        # cfg 3: m 16 x 16, width 64, per-GPU batch 32
+    (5, 64, 64, (40, 40), (4, 6), True),           # partly filled batch chunk
+    (70, 48, 64, (40, 40), (3, 4), True),          # three batch chunks (32 + 32 + 6), Ci != Co
+    (33, 64, 40, (40, 40), (5, 2), True),
+    (3, 37, 61, (24, 24), (2, 8), True),           # channel counts that are not multiples of 4 / 8
+    (4, 64, 64, (12, 12, 14), (2, 3, 4), True),    # 3-D corners
+    (3, 64, 64, (40, 40), (4, 5), False),          # odd innermost mode count -> FP32 kernel
+    (3, 32, 32, (40, 40), (4, 4), False),          # width 32 -> FP32 kernel
+])
+def test_mix_tensor_core(lib, B, Ci, Co, spatial, modes, tc):
+    rng = np.random.default_rng(B * 1000 + Ci * 7 + Co)
+    nd = len(spatial)
+    plan = lib.get_plan(torch.device("cuda", 0), spatial, modes)
+    assert lib.mix_tc_supported(plan, Ci, Co) == tc
+    ws = [cplx(rng, (Ci, Co) + tuple(modes), scale=0.5) for _ in range(2 if nd == 2 else 4)]
+    X = cplx(rng, (B, Ci) + plan.spec_shape)
+    gY = cplx(rng, (B, Co) + plan.spec_shape)
+    wt = [dev(w) for w in ws]
+    wcat = O.cat_corner_weights(ws)
+    Y = lib.mix_fwd(plan, dev(X), wt).cpu().numpy()
+    assert O.rel_err(Y, O.mix_fwd(X.astype(np.complex128), wcat)) < TOL
+    gX, gws = lib.mix_bwd(plan, dev(X), dev(gY), wt)
+    gx_ref, gw_ref = O.mix_bwd(X.astype(np.complex128), gY.astype(np.complex128), wcat)
+    assert O.rel_err(gX.cpu().numpy(), gx_ref) < TOL
+    for got, ref in zip(gws, O.split_corner_grads(gw_ref, len(ws))):
+        assert O.rel_err(got.cpu().numpy(), ref) < TOL
+    # per-mode errors too: a wrong mode pair / corner would hide behind a global max
+    err = np.abs(Y - O.mix_fwd(X.astype(np.complex128), wcat)).reshape(B, Co, -1).max(axis=(0, 1))
+    assert err.max() < 1e-5 * np.abs(Y).max()
+
+
+@pytest.mark.parametrize("low", ["tf32", "bf16"])
+def test_mix_tensor_core_math_modes(lib, low):
+    """tf32 / bf16 modes reach K2's tensor-core kernels: single pass, stated bounds 2e-3 / 2e-2, visibly worse than fp32."""
+    rng = np.random.default_rng(5)
+    B, C, modes = 16, 64, (8, 8)
+    plan = lib.get_plan(torch.device("cuda", 0), (34, 34), modes)
+    ws = [cplx(rng, (C, C) + modes, scale=0.5) for _ in range(2)]
+    X, gY = cplx(rng, (B, C) + plan.spec_shape), cplx(rng, (B, C) + plan.spec_shape)
+    wcat = O.cat_corner_weights(ws)
+    y_ref = O.mix_fwd(X.astype(np.complex128), wcat)
+    gx_ref, gw_ref = O.mix_bwd(X.astype(np.complex128), gY.astype(np.complex128), wcat)
+    errs = {}
+    for mode in (low, "fp32"):
+        prev = lib.set_math_mode(mode)
+        try:
+            Y = lib.mix_fwd(plan, dev(X), [dev(w) for w in ws])
+            gX, gws = lib.mix_bwd(plan, dev(X), dev(gY), [dev(w) for w in ws])
+            torch.cuda.synchronize()
+        finally:
+            lib.set_math_mode(prev)
+        errs[mode] = max(O.rel_err(Y.cpu().numpy(), y_ref), O.rel_err(gX.cpu().numpy(), gx_ref),
+                         max(O.rel_err(g.cpu().numpy(), r) for g, r in zip(gws, O.split_corner_grads(gw_ref, 2))))
+    assert errs["fp32"] < TOL, errs
+    assert errs[low] < {"tf32": 2e-3, "bf16": 2e-2}[low], errs
+    assert errs[low] > 4 * errs["fp32"], errs
+
+
 @pytest.mark.parametrize("B,Co,Ci,spatial", [
     (2, 20, 20, (130, 130)),
     (3, 8, 8, (13, 11)),         # N not a multiple of 4 -> scalar path
