@@ -82,6 +82,9 @@ int launch_mix_bwd_data(const Plan* p, const float* gY, const float* const* w, f
 int launch_mix_bwd_weight(const Plan* p, const float* X, const float* gY, float* const* gw, int B,
                           int Ci, int Co, cudaStream_t st);
 bool mix_tc_supported(const Plan* p, int Ci, int Co);
+bool pointwise_tc_supported(int Cin, int Cout);
+int launch_pointwise_tc(const float* in, const float* W, const float* bias, float* out, int B, int Co, int Ci, long N,
+                        int transpose, cudaStream_t st);
 
 // ---- device helpers --------------------------------------------------------------------------
 // exact unsigned 32-bit division by a run-time constant (Granlund-Montgomery): 4 instructions instead

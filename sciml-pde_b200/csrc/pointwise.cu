@@ -611,6 +611,8 @@ extern "C" int fno_pointwise_fwd(const float* in, const float* W, const float* b
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Cout = transpose ? Ci : Co;
   const int Cin = transpose ? Co : Ci;
+  // wide layers (width 33..64, cfg 3): the product and its data gradient run on tcgen05 (pointwise_tc.cu)
+  if (pointwise_tc_supported(Cin, Cout)) return launch_pointwise_tc(in, W, bias, out, B, Co, Ci, N, transpose, st);
   const bool vec2 = (N % 2 == 0) && ((reinterpret_cast<size_t>(in) | reinterpret_cast<size_t>(out)) % 8 == 0);
   if (vec2 && Cin <= 256) {
     if (Cout % 20 == 0) return launch_pw2<20>(in, W, bias, out, B, Co, Ci, N, transpose, st);
