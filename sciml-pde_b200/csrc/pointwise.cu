@@ -708,6 +708,16 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
     count_launch();
     return check_launch("wgrad_reduce_kernel");
   }
+  if (aligned && pointwise_tc_supported(Ci, Co)) {
+    // wide channels on tcgen05: [ds ; a] [a ; 1]^T per 64-pixel slab, accumulator in TMEM (pointwise_tc.cu)
+    int nparts = 0;
+    int rct = launch_wgrad_tc(ds, a, part, B, Co, Ci, N, WG_CTAS, &nparts, st);
+    if (rct != FNO_OK) return rct;
+    const int totalo = Co * (Ci + 1);
+    wgrad_reduce_kernel<<<(totalo * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, nparts, Co, Ci);
+    count_launch();
+    return check_launch("wgrad_reduce_kernel");
+  }
   if (aligned && ygroups > 1 && Co <= WW_C && Ci <= WW_C) {
     // wide channels: one CTA owns the whole Co x Ci output (wgrad_wide_kernel)
     const size_t smemw = sizeof(float) * 2ul * 2 * WW_C * WW_P;

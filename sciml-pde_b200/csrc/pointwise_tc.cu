@@ -179,6 +179,191 @@ pointwise_tc_kernel(const float* __restrict__ in, const float* __restrict__ W, c
   if (warp == PT_EPI_WARPS) tmem_dealloc(tmem_base, 2 * PT_N);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Weight / bias gradient of the wide 1x1 conv:  gW[o, i] = sum_{b,p} ds[b, o, p] a[b, i, p],  gb[o] = sum ds[b, o, p].
+// The contraction runs over PIXELS, which are contiguous in both tensors, so a 64-pixel slab of [ds ; a] is already
+// K-major: thread = (channel row, 16-byte pixel chunk) loads one float4, splits it and stores hi / lo into ONE stacked
+// operand buffer  rows 0..63 = ds channels, 64..127 = a channels, 128..143 = a constant row of ones + zero padding
+// (LBO = 144 B: the chunk-strided 16-byte stores of a quarter warp are conflict-free).  A = rows 0..127 and
+// B = rows 64..143 of that same buffer:
+//     D[128 x 80] += [ds ; a] [a ; 1]^T        M = 128, N = 80, K = 8 x 8 pixels per slab, 3xTF32
+// rows 0..63 of D are gW (columns 0..63) and gb (column 64); rows 64..127 (a a^T) are the price of not staging a second
+// operand -- the tensor pipe has the room (24 MMAs ~ 0.8 k cycles per slab against ~1.5 k cycles of HBM time).
+// The tensor core's fp32 accumulate truncates: a chain of ~500 MMAs into one TMEM tile measured 7e-6 of relative error
+// (biased, so it grows with the chain), too much for the 1e-5 fp32-mode bound.  A TMEM tile therefore only collects
+// WT_CHAIN = 2 slabs (48 MMAs); the loader warps drain it into IEEE fp32 register accumulators while the next chain fills
+// the other tile.  Per-CTA partials go through wgrad_reduce_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int WT_KT = 64;                        // pixels per slab
+constexpr int WT_LBO = 144;
+constexpr int WT_SBO = (WT_KT / 4) * WT_LBO;     // 2304
+constexpr int WT_ROWS = 144;
+constexpr int WT_BUF = (WT_ROWS / 8) * WT_SBO;   // 41 472 bytes per hi / lo buffer
+constexpr int WT_N = 80;
+constexpr int WT_LD_WARPS = 16;
+constexpr int WT_THREADS = 32 * WT_LD_WARPS + 32;
+constexpr int WT_SMEM = 4 * WT_BUF + 8 * 8 + 16;
+
+__global__ void __launch_bounds__(WT_THREADS, 1)
+wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co, int Ci, long N,
+                int slabs_per_sample, long total_slabs, long slabs_per_cta, int single) {
+  FNO_SPLIT_CONSTS(single);
+  extern __shared__ __align__(128) unsigned char wsm[];
+  unsigned char* b_hi = wsm;                     // [2 stages][WT_BUF]
+  unsigned char* b_lo = wsm + 2 * WT_BUF;
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(wsm + 4 * WT_BUF);
+  unsigned long long* a_ready = bars;            // [2] loaders -> MMA
+  unsigned long long* a_free = bars + 2;         // [2] MMA -> loaders
+  unsigned long long* d_full = bars + 4;         // [2] MMA -> drain: a chain of two slabs has landed in D[chain & 1]
+  unsigned long long* d_free = bars + 6;         // [2] drain -> MMA
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 8);
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(a_ready + s, WT_LD_WARPS);
+      mbar_init(a_free + s, 1);
+      mbar_init(d_full + s, 1);
+      mbar_init(d_free + s, WT_LD_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WT_LD_WARPS) tmem_alloc(tmem_slot, 256);
+  // constant rows 128..143 of both stages: row 128 = ones (hi = 1, lo = 0), the rest zero
+  for (int i = tid; i < 2 * 16 * WT_KT; i += WT_THREADS) {
+    const int s = i / (16 * WT_KT), r = 128 + (i / WT_KT) % 16, k = i % WT_KT;
+    const int off = s * WT_BUF + (r & 7) * 16 + (r >> 3) * WT_SBO + (k >> 2) * WT_LBO + (k & 3) * 4;
+    *reinterpret_cast<float*>(b_hi + off) = r == 128 ? 1.0f : 0.0f;
+    *reinterpret_cast<float*>(b_lo + off) = 0.0f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const long s_begin = (long)blockIdx.x * slabs_per_cta;
+  long s_end = s_begin + slabs_per_cta;
+  if (s_end > total_slabs) s_end = total_slabs;
+  const int n = s_end > s_begin ? (int)(s_end - s_begin) : 0;
+
+  if (warp == WT_LD_WARPS) {
+    constexpr unsigned idesc = umma_idesc_tf32(128, WT_N, 0, 0);
+    for (int it = 0; it < n; ++it) {
+      const int st = it & 1;                       // operand stage = position inside the chain
+      const int c = it >> 1, db = c & 1;           // chain and its TMEM tile
+      mbar_wait(a_ready + st, (unsigned)c & 1u);
+      if (st == 0 && c >= 2) mbar_wait(d_free + db, (unsigned)((c >> 1) - 1) & 1u);   // chain c-2 drained
+      tc_fence_after();
+      __syncwarp();
+      const unsigned long long a_h = umma_desc(b_hi + st * WT_BUF, WT_LBO, WT_SBO), a_l = umma_desc(b_lo + st * WT_BUF, WT_LBO, WT_SBO);
+      const unsigned long long bo = (unsigned long long)((8 * WT_SBO) >> 4);       // B = rows 64..143
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass)              // lo*hi, hi*lo, hi*hi
+#pragma unroll
+        for (int ks = 0; ks < WT_KT / 8; ++ks)
+          if (pass == 2 || !single)
+            tc_mma_tf32_elect(tmem_base + (unsigned)(128 * db),
+                              (pass == 0 ? a_l : a_h) + (unsigned long long)(ks * (2 * WT_LBO >> 4)),
+                              (pass == 1 ? a_l : a_h) + bo + (unsigned long long)(ks * (2 * WT_LBO >> 4)), idesc,
+                              (st != 0 || ks != 0 || (!single && pass != 0)) ? 1u : 0u);
+      tc_commit_elect(a_free + st);
+      if (st == 1 || it == n - 1) tc_commit_elect(d_full + db);
+    }
+  } else {
+    const int q = tid & 15;                        // 16-byte pixel chunk of the slab
+    const int r0 = tid >> 4;                       // rows r0 + 32 u
+    float4 raw[2][4];
+    auto load_raw = [&](int it, float4 (&v)[4]) {
+      const long slab = s_begin + it;
+      const bool inr = it < n;
+      const long b = inr ? slab / slabs_per_sample : 0;
+      const long k = inr ? (slab - b * slabs_per_sample) * WT_KT + 4 * q : 0;
+      const bool pv = inr && k < N;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + 32 * u;
+        const bool is_ds = r < 64;
+        const int ch = is_ds ? r : r - 64;
+        const int C = is_ds ? Co : Ci;
+        const float* src = (is_ds ? ds : a) + ((size_t)b * C + ch) * N + k;
+        v[u] = (pv && ch < C) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto store_raw = [&](int st, const float4 (&v)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = r0 + 32 * u;
+        const int off = st * WT_BUF + (r & 7) * 16 + (r >> 3) * WT_SBO + q * WT_LBO;
+        float4 hi, lo;
+        split_rm(v[u].x, hi.x, lo.x, sp_rnd, sp_msk);
+        split_rm(v[u].y, hi.y, lo.y, sp_rnd, sp_msk);
+        split_rm(v[u].z, hi.z, lo.z, sp_rnd, sp_msk);
+        split_rm(v[u].w, hi.w, lo.w, sp_rnd, sp_msk);
+        *reinterpret_cast<float4*>(b_hi + off) = hi;
+        if (!single) *reinterpret_cast<float4*>(b_lo + off) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_ready + st);
+    };
+    // rows 0..63 of D (TMEM lanes 0..63: quadrants 0, 1) are gW | gb: warp <-> (quadrant, 16 columns), IEEE accumulators
+    const int quad = warp & 3, colq = warp >> 2;
+    float accw[16], accb = 0.f;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) accw[e] = 0.f;
+    const int nchains = (n + 1) >> 1;
+    int drained = 0;
+    auto drain = [&]() {                           // chain `drained`: D[drained & 1] -> registers, tile handed back
+      const int db = drained & 1;
+      mbar_wait(d_full + db, (unsigned)(drained >> 1) & 1u);
+      tc_fence_after();
+      if (quad < 2) {
+        float v[16];
+        tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(128 * db + 16 * colq), v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) accw[e] += v[e];
+        if (colq == 0) {
+          float w[8];
+          tmem_ld8(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(128 * db + 64), w);
+          accb += w[0];
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_free + db);
+      ++drained;
+    };
+    load_raw(0, raw[0]);
+    load_raw(1, raw[1]);
+    for (int it = 0; it < n; it += 2) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = it + h;
+        if (i < n) {
+          if (i >= 2) mbar_wait(a_free + h, (unsigned)((i >> 1) - 1) & 1u);   // slab i-2's MMAs have read stage h
+          store_raw(h, raw[h]);
+          load_raw(i + 2, raw[h]);
+          if (h == 1 && i >= 3) drain();           // chain (i - 3) / 2 finished a whole slab ago: no wait in practice
+        }
+      }
+    }
+    while (drained < nchains) drain();
+    if (quad < 2) {
+      const int o = quad * 32 + lane;
+      float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
+      if (o < Co) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e)
+          if (16 * colq + e < Ci) pp[(size_t)o * (Ci + 1) + 16 * colq + e] = accw[e];
+        if (colq == 0) pp[(size_t)o * (Ci + 1) + Ci] = accb;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WT_LD_WARPS) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace
 
 bool pointwise_tc_supported(int Cin, int Cout) {
@@ -204,6 +389,28 @@ int launch_pointwise_tc(const float* in, const float* W, const float* bias, floa
                                                          g_math_mode.load());
   count_launch();
   return check_launch("pointwise_tc_kernel");
+}
+
+// per-CTA partial records [ctas][Co][Ci + 1] into `part` (the caller runs wgrad_reduce_kernel over them); returns the
+// number of records through *nparts.  Needs N % 4 == 0 and 16-byte aligned tensors (the caller checks).
+int launch_wgrad_tc(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts, int* nparts,
+                    cudaStream_t st) {
+  static PerDeviceOnce done;
+  if (done.need()) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(wgrad_tc)");
+    done.mark();
+  }
+  const int sps = (int)((N + WT_KT - 1) / WT_KT);
+  const long total = (long)B * sps;
+  long ctas = total < 148 ? total : 148;
+  if (ctas > max_parts) ctas = max_parts;
+  const long spc = (total + ctas - 1) / ctas;
+  ctas = (total + spc - 1) / spc;
+  wgrad_tc_kernel<<<(unsigned)ctas, WT_THREADS, WT_SMEM, st>>>(ds, a, part, Co, Ci, N, sps, total, spc, g_math_mode.load());
+  count_launch();
+  *nparts = (int)ctas;
+  return check_launch("wgrad_tc_kernel");
 }
 
 }  // namespace fno
