@@ -707,7 +707,8 @@ def test_new_entry_points_reject_bad_arguments(lib):
     assert L.fno_set_math_mode(7) < 0
     assert lib.get_math_mode() == "fp32"
     with pytest.raises(lib.FnoError):
-        lib.set_math_mode("bf16")
+        lib.set_math_mode("fp8")          # only fp32 / tf32 / bf16 exist
+    assert lib.get_math_mode() == "fp32"
     # device-resident dataset: trajectories shorter than a window
     from fno_b200 import data
     with pytest.raises(ValueError):
