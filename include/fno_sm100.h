@@ -221,6 +221,19 @@ int fno_head_bwd_tc(const float* h, const float* dout, const float* W1, const fl
                     float* gW2, float* gb2, void* work, int B, int R_in, int W_in, int R_out, int Wp,
                     int C, int HID, int V, fno_stream_t stream);
 
+/* Wide trunks (24 <= C <= 64; BASELINE configs[2]: width 64), same contract in two tcgen05 launches
+ * (head_wide_tc.cu): the hidden-layer recompute + dpre + dh = dpre W1 per 128 positions of the padded
+ * plane (h and dpre as A operands in tensor memory), then gW1 | gb1 = dpre^T [h ; 1] with the pixels
+ * as K; dpre [B, 128, R_out*Wp] passes through `work`.  Requires HID = 128, V <= 4 and
+ * (R_out * Wp) % 4 == 0 (fno_head_bwd_wide_supported); work:
+ * fno_head_bwd_wide_workspace_bytes(B, R_out, Wp, C, V) bytes, 16-byte aligned.                     */
+int fno_head_bwd_wide_supported(int R_out, int Wp, int C, int HID, int V);
+size_t fno_head_bwd_wide_workspace_bytes(int B, int R_out, int Wp, int C, int V);
+int fno_head_bwd_wide_tc(const float* h, const float* dout, const float* W1, const float* b1,
+                         const float* W2, const float* stats, float* dh, float* gW1, float* gb1,
+                         float* gW2, float* gb2, void* work, int B, int R_in, int W_in, int R_out,
+                         int Wp, int C, int HID, int V, fno_stream_t stream);
+
 /* ---- device-resident windowed dataset ----------------------------------------- */
 /* Replaces the per-item HDF5 read + host-side slicing of the reference loaders
  * (fno/utils_2d_rd_baseline.py:59-102): traj [n_traj, pixels, T, V] stays on the GPU (time-inner), item b of

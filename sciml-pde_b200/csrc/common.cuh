@@ -83,6 +83,9 @@ int launch_mix_bwd_weight(const Plan* p, const float* X, const float* gY, float*
                           int Ci, int Co, cudaStream_t st);
 bool mix_tc_supported(const Plan* p, int Ci, int Co);
 bool pointwise_tc_supported(int Cin, int Cout);
+int launch_wgrad_tc_rows128(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts,
+                            int* nparts, cudaStream_t st);
+int launch_wgrad_reduce(const float* part, float* gW, float* gb, int nparts, int Co, int Ci, cudaStream_t st);
 int launch_wgrad_tc(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts, int* nparts,
                     cudaStream_t st);
 int launch_pointwise_tc(const float* in, const float* W, const float* bias, float* out, int B, int Co, int Ci, long N,

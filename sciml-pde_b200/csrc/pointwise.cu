@@ -597,6 +597,13 @@ wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gW, floa
 constexpr int WG_CTAS = 148 * 2;  // persistent grid: 2 resident CTAs per SM (register-limited)
 
 }  // namespace
+
+int launch_wgrad_reduce(const float* part, float* gW, float* gb, int nparts, int Co, int Ci, cudaStream_t st) {
+  const int total = Co * (Ci + 1);
+  wgrad_reduce_kernel<<<(total * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, nparts, Co, Ci);
+  count_launch();
+  return check_launch("wgrad_reduce_kernel");
+}
 }  // namespace fno
 
 using namespace fno;

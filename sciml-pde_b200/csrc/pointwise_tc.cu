@@ -195,20 +195,30 @@ pointwise_tc_kernel(const float* __restrict__ in, const float* __restrict__ W, c
 // WT_CHAIN = 2 slabs (48 MMAs); the loader warps drain it into IEEE fp32 register accumulators while the next chain fills
 // the other tile.  Per-CTA partials go through wgrad_reduce_kernel.
 // ------------------------------------------------------------------------------------------
-constexpr int WT_KT = 64;                        // pixels per slab
+// RA = rows of the gradient (64: the bypass; 128: the projection head's hidden layer, head_wide_tc.cu -- then A is the
+// ds block alone and B = [a ; 1]), KT = pixels per slab (64 / 32: the stacked buffer must fit twice, hi and lo).
 constexpr int WT_LBO = 144;
-constexpr int WT_SBO = (WT_KT / 4) * WT_LBO;     // 2304
-constexpr int WT_ROWS = 144;
-constexpr int WT_BUF = (WT_ROWS / 8) * WT_SBO;   // 41 472 bytes per hi / lo buffer
 constexpr int WT_N = 80;
 constexpr int WT_LD_WARPS = 16;
 constexpr int WT_THREADS = 32 * WT_LD_WARPS + 32;
-constexpr int WT_SMEM = 4 * WT_BUF + 8 * 8 + 16;
+template <int RA, int KT>
+struct WtCfg {
+  static constexpr int SBO = (KT / 4) * WT_LBO;          // 2304 / 1152
+  static constexpr int ROWS = RA + 80;                   // ds | a (64) | ones + zero padding (16)
+  static constexpr int BUF = (ROWS / 8) * SBO;           // bytes per hi / lo buffer
+  static constexpr int SMEM = 4 * BUF + 8 * 8 + 16;
+  static constexpr int RPP = (32 * WT_LD_WARPS) / (KT / 4);   // rows staged per pass of the loader threads
+  static constexpr int NU = (RA + 64) / RPP;             // passes
+  static_assert((RA + 64) % RPP == 0, "loader mapping");
+};
 
+template <int RA, int KT>
 __global__ void __launch_bounds__(WT_THREADS, 1)
 wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co, int Ci, long N,
                 int slabs_per_sample, long total_slabs, long slabs_per_cta, int single) {
   FNO_SPLIT_CONSTS(single);
+  using Cfg = WtCfg<RA, KT>;
+  constexpr int WT_KT = KT, WT_SBO = Cfg::SBO, WT_BUF = Cfg::BUF;
   extern __shared__ __align__(128) unsigned char wsm[];
   unsigned char* b_hi = wsm;                     // [2 stages][WT_BUF]
   unsigned char* b_lo = wsm + 2 * WT_BUF;
@@ -229,11 +239,11 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WT_LD_WARPS) tmem_alloc(tmem_slot, 256);
-  // constant rows 128..143 of both stages: row 128 = ones (hi = 1, lo = 0), the rest zero
+  // constant rows RA+64 .. RA+79 of both stages: the first = ones (hi = 1, lo = 0), the rest zero
   for (int i = tid; i < 2 * 16 * WT_KT; i += WT_THREADS) {
-    const int s = i / (16 * WT_KT), r = 128 + (i / WT_KT) % 16, k = i % WT_KT;
+    const int s = i / (16 * WT_KT), r = RA + 64 + (i / WT_KT) % 16, k = i % WT_KT;
     const int off = s * WT_BUF + (r & 7) * 16 + (r >> 3) * WT_SBO + (k >> 2) * WT_LBO + (k & 3) * 4;
-    *reinterpret_cast<float*>(b_hi + off) = r == 128 ? 1.0f : 0.0f;
+    *reinterpret_cast<float*>(b_hi + off) = r == RA + 64 ? 1.0f : 0.0f;
     *reinterpret_cast<float*>(b_lo + off) = 0.0f;
   }
   fence_proxy_async();
@@ -256,7 +266,7 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
       tc_fence_after();
       __syncwarp();
       const unsigned long long a_h = umma_desc(b_hi + st * WT_BUF, WT_LBO, WT_SBO), a_l = umma_desc(b_lo + st * WT_BUF, WT_LBO, WT_SBO);
-      const unsigned long long bo = (unsigned long long)((8 * WT_SBO) >> 4);       // B = rows 64..143
+      const unsigned long long bo = (unsigned long long)(((RA / 8) * WT_SBO) >> 4);   // B = rows RA .. RA+79
 #pragma unroll
       for (int pass = 0; pass < 3; ++pass)              // lo*hi, hi*lo, hi*hi
 #pragma unroll
@@ -270,29 +280,30 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
       if (st == 1 || it == n - 1) tc_commit_elect(d_full + db);
     }
   } else {
-    const int q = tid & 15;                        // 16-byte pixel chunk of the slab
-    const int r0 = tid >> 4;                       // rows r0 + 32 u
-    float4 raw[2][4];
-    auto load_raw = [&](int it, float4 (&v)[4]) {
+    const int q = tid % (KT / 4);                  // 16-byte pixel chunk of the slab
+    const int r0 = tid / (KT / 4);                 // rows r0 + RPP u
+    constexpr int NU = Cfg::NU;
+    float4 raw[2][NU];
+    auto load_raw = [&](int it, float4 (&v)[NU]) {
       const long slab = s_begin + it;
       const bool inr = it < n;
       const long b = inr ? slab / slabs_per_sample : 0;
       const long k = inr ? (slab - b * slabs_per_sample) * WT_KT + 4 * q : 0;
       const bool pv = inr && k < N;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + 32 * u;
-        const bool is_ds = r < 64;
-        const int ch = is_ds ? r : r - 64;
+      for (int u = 0; u < NU; ++u) {
+        const int r = r0 + Cfg::RPP * u;
+        const bool is_ds = r < RA;
+        const int ch = is_ds ? r : r - RA;
         const int C = is_ds ? Co : Ci;
         const float* src = (is_ds ? ds : a) + ((size_t)b * C + ch) * N + k;
         v[u] = (pv && ch < C) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    auto store_raw = [&](int st, const float4 (&v)[4]) {
+    auto store_raw = [&](int st, const float4 (&v)[NU]) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int r = r0 + 32 * u;
+      for (int u = 0; u < NU; ++u) {
+        const int r = r0 + Cfg::RPP * u;
         const int off = st * WT_BUF + (r & 7) * 16 + (r >> 3) * WT_SBO + q * WT_LBO;
         float4 hi, lo;
         split_rm(v[u].x, hi.x, lo.x, sp_rnd, sp_msk);
@@ -306,7 +317,8 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready + st);
     };
-    // rows 0..63 of D (TMEM lanes 0..63: quadrants 0, 1) are gW | gb: warp <-> (quadrant, 16 columns), IEEE accumulators
+    // rows 0..RA-1 of D (TMEM lanes 0..RA-1) are gW | gb: warp <-> (quadrant, 16 columns), IEEE accumulators
+    constexpr int NQ = RA / 32;
     const int quad = warp & 3, colq = warp >> 2;
     float accw[16], accb = 0.f;
 #pragma unroll
@@ -317,7 +329,7 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
       const int db = drained & 1;
       mbar_wait(d_full + db, (unsigned)(drained >> 1) & 1u);
       tc_fence_after();
-      if (quad < 2) {
+      if (quad < NQ) {
         float v[16];
         tmem_ld16(tmem_base + ((unsigned)(quad * 32) << 16) + (unsigned)(128 * db + 16 * colq), v);
 #pragma unroll
@@ -348,7 +360,7 @@ wgrad_tc_kernel(const float* __restrict__ ds, const float* __restrict__ a, float
       }
     }
     while (drained < nchains) drain();
-    if (quad < 2) {
+    if (quad < NQ) {
       const int o = quad * 32 + lane;
       float* __restrict__ pp = part + (size_t)blockIdx.x * Co * (Ci + 1);
       if (o < Co) {
@@ -393,24 +405,38 @@ int launch_pointwise_tc(const float* in, const float* W, const float* bias, floa
 
 // per-CTA partial records [ctas][Co][Ci + 1] into `part` (the caller runs wgrad_reduce_kernel over them); returns the
 // number of records through *nparts.  Needs N % 4 == 0 and 16-byte aligned tensors (the caller checks).
-int launch_wgrad_tc(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts, int* nparts,
-                    cudaStream_t st) {
+template <int RA, int KT>
+static int launch_wgrad_tc_t(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts,
+                             int* nparts, cudaStream_t st) {
+  using Cfg = WtCfg<RA, KT>;
   static PerDeviceOnce done;
   if (done.need()) {
-    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WT_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(wgrad_tc_kernel<RA, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(wgrad_tc)");
     done.mark();
   }
-  const int sps = (int)((N + WT_KT - 1) / WT_KT);
+  const int sps = (int)((N + KT - 1) / KT);
   const long total = (long)B * sps;
   long ctas = total < 148 ? total : 148;
   if (ctas > max_parts) ctas = max_parts;
   const long spc = (total + ctas - 1) / ctas;
   ctas = (total + spc - 1) / spc;
-  wgrad_tc_kernel<<<(unsigned)ctas, WT_THREADS, WT_SMEM, st>>>(ds, a, part, Co, Ci, N, sps, total, spc, g_math_mode.load());
+  wgrad_tc_kernel<RA, KT><<<(unsigned)ctas, WT_THREADS, Cfg::SMEM, st>>>(ds, a, part, Co, Ci, N, sps, total, spc,
+                                                                        g_math_mode.load());
   count_launch();
   *nparts = (int)ctas;
   return check_launch("wgrad_tc_kernel");
+}
+
+int launch_wgrad_tc(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts, int* nparts,
+                    cudaStream_t st) {
+  return launch_wgrad_tc_t<64, 64>(ds, a, part, B, Co, Ci, N, max_parts, nparts, st);
+}
+
+// Co <= 128 gradient rows (the projection head's hidden layer), Ci <= 64
+int launch_wgrad_tc_rows128(const float* ds, const float* a, float* part, int B, int Co, int Ci, long N, int max_parts,
+                            int* nparts, cudaStream_t st) {
+  return launch_wgrad_tc_t<128, 32>(ds, a, part, B, Co, Ci, N, max_parts, nparts, st);
 }
 
 }  // namespace fno

@@ -14,7 +14,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR.parent / "csrc"
 OBJ_DIR = PKG_DIR.parent / "build"
 LIB_PATH = PKG_DIR / "libfno_sm100.so"
-SOURCES = ["api.cu", "transform2d.cu", "mix.cu", "pointwise.cu", "axis3d.cu", "headlift.cu", "steptail.cu", "head_tc.cu", "transform2d_tc.cu", "head_bwd_tc.cu", "dataset.cu", "layer2d_tc.cu", "metrics.cu", "spectral1d.cu", "pointwise_tc.cu"]
+SOURCES = ["api.cu", "transform2d.cu", "mix.cu", "pointwise.cu", "axis3d.cu", "headlift.cu", "steptail.cu", "head_tc.cu", "transform2d_tc.cu", "head_bwd_tc.cu", "dataset.cu", "layer2d_tc.cu", "metrics.cu", "spectral1d.cu", "pointwise_tc.cu", "head_wide_tc.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "tc_common.cuh", PKG_DIR.parent.parent / "include" / "fno_sm100.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

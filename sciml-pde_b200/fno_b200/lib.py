@@ -91,6 +91,9 @@ def load():
             "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
             "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
             "fno_head_bwd_tc": (i, [vp] * 12 + [i] * 8 + [vp]),
+            "fno_head_bwd_wide_supported": (i, [i, i, i, i, i]),
+            "fno_head_bwd_wide_workspace_bytes": (C.c_size_t, [i, i, i, i, i]),
+            "fno_head_bwd_wide_tc": (i, [vp] * 12 + [i] * 8 + [vp]),
             "fno_nrmse_workspace_bytes": (C.c_size_t, [i, i]),
             "fno_nrmse_fwd": (i, [vp, vp, vp, vp, i, l, i, vp]),
             "fno_nrmse_bwd": (i, [vp, vp, vp, vp, vp, i, l, i, vp]),
@@ -121,6 +124,7 @@ EXPORTED_SYMBOLS = (
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad", "fno_pointwise_bwd",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
     "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
+    "fno_head_bwd_wide_supported", "fno_head_bwd_wide_workspace_bytes", "fno_head_bwd_wide_tc",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
     "fno_metric_workspace_bytes", "fno_metric_func", "fno_window_shift",
@@ -587,16 +591,21 @@ def head_bwd(geo: TrunkGeo, h, dout, W1, b1, W2, stats):
     _require(dout, torch.float32, "dout")
     B, C, HID, V = h.shape[0], h.shape[1], W1.shape[0], W2.shape[0]
     lib = load()
-    work = torch.empty(lib.fno_head_bwd_workspace_bytes(C, HID, V) // 4, dtype=torch.float32, device=h.device)
     dh = torch.empty_like(h)
     gW1, gb1 = torch.empty_like(W1), torch.empty(HID, dtype=torch.float32, device=h.device)
     gW2, gb2 = torch.empty_like(W2), torch.empty(V, dtype=torch.float32, device=h.device)
     tc = HEAD_BWD_TC and HID == 128 and C <= 23 and V <= 8
-    fn = lib.fno_head_bwd_tc if tc else lib.fno_head_bwd      # tcgen05 3xTF32 path / FP32 CUDA-core path
+    # wide trunks (24 <= C <= 64, cfg 3): two tcgen05 launches with the hidden-layer gradient passing through HBM
+    wide = HEAD_BWD_TC and not tc and bool(lib.fno_head_bwd_wide_supported(geo.R_out, geo.Wp, C, HID, V))
+    if wide:
+        nbytes, fn, name = lib.fno_head_bwd_wide_workspace_bytes(B, geo.R_out, geo.Wp, C, V), lib.fno_head_bwd_wide_tc, "fno_head_bwd_wide_tc"
+    else:
+        nbytes = lib.fno_head_bwd_workspace_bytes(C, HID, V)
+        fn, name = (lib.fno_head_bwd_tc, "fno_head_bwd_tc") if tc else (lib.fno_head_bwd, "fno_head_bwd")   # tcgen05 3xTF32 / FP32
+    work = torch.empty(nbytes // 4, dtype=torch.float32, device=h.device)
     _check(fn(h.data_ptr(), dout.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(),
               stats.data_ptr(), dh.data_ptr(), gW1.data_ptr(), gb1.data_ptr(), gW2.data_ptr(),
-              gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
-           "fno_head_bwd_tc" if tc else "fno_head_bwd")
+              gb2.data_ptr(), work.data_ptr(), B, *geo.ints, C, HID, V, _stream()), name)
     return dh, gW1, gb1, gW2, gb2
 
 

@@ -449,6 +449,12 @@ HEAD_CASES = [
     ((16, 16, 22), 20, 5, 2),   # cfg-4 shape class: 5 variables (tensor-core heads with 8-wide variable rows), many tiles
     ((30, 34), 12, 8, 2),       # V = 8: the widest tensor-core case
     ((20, 20), 8, 7, 1),
+    # wide trunks (24 <= C <= 64): head_bwd_wide_kernel + wgrad_tc_kernel<128, 32> when the padded plane is a multiple of 4
+    ((256, 256), 64, 3, 1),     # cfg-3 plane: 521 position tiles per sample, 2081 pixel slabs
+    ((40, 50), 48, 2, 3),       # C not a multiple of 16, several samples, ragged last tile
+    ((30, 33), 24, 4, 2),       # narrowest wide case, V = 4
+    ((6, 6, 10), 40, 3, 2),     # 3-D trunk layout (rows = X * Y, last axis padded by 6)
+    ((9, 11), 64, 3, 2),        # padded plane 11 x 13: not a multiple of 4 -> FP32 kernels
 ]
 
 
@@ -456,15 +462,17 @@ HEAD_CASES = [
 @pytest.mark.parametrize("spatial,C,V,B", HEAD_CASES)
 def test_head_forward_backward(lib, monkeypatch, spatial, C, V, B, bwd_tc):
     monkeypatch.setattr(lib, "HEAD_BWD_TC", bwd_tc)
-    if bwd_tc and (C > 23 or V > 8):
-        pytest.skip("outside the tensor-core backward's envelope (FP32 path covers it)")
+    nd = len(spatial)
+    pad = 2 if nd == 2 else 6
+    geo = lib.TrunkGeo(spatial, pad)
+    wide = bool(lib.load().fno_head_bwd_wide_supported(geo.R_out, geo.Wp, C, 128, V))
+    assert wide == (24 <= C <= 64 and V <= 4 and (geo.R_out * geo.Wp) % 4 == 0)
+    if bwd_tc and (C > 23 or V > 8) and not wide:
+        pytest.skip("outside the tensor-core backward's envelopes (FP32 path covers it)")
     from fno_b200 import ops
     from oracle import fno_port as P
 
     g = torch.Generator().manual_seed(5)
-    nd = len(spatial)
-    pad = 2 if nd == 2 else 6
-    geo = lib.TrunkGeo(spatial, pad)
     h = torch.randn((B, C) + geo.padded, generator=g) * 1.5
     W1 = torch.randn(128, C, generator=g) / C ** 0.5
     b1 = torch.randn(128, generator=g) * 0.3
