@@ -226,7 +226,11 @@ int fno_head_bwd_tc(const float* h, const float* dout, const float* W1, const fl
  * plane (h and dpre as A operands in tensor memory), then gW1 | gb1 = dpre^T [h ; 1] with the pixels
  * as K; dpre [B, 128, R_out*Wp] passes through `work`.  Requires HID = 128, V <= 4 and
  * (R_out * Wp) % 4 == 0 (fno_head_bwd_wide_supported); work:
- * fno_head_bwd_wide_workspace_bytes(B, R_out, Wp, C, V) bytes, 16-byte aligned.                     */
+ * fno_head_bwd_wide_workspace_bytes(B, R_out, Wp, C, V) bytes, 16-byte aligned.
+ * fno_head_fwd_wide_tc: the forward (contract of fno_head_fwd) for HID = 128, C <= 64, V <= 4.     */
+int fno_head_fwd_wide_tc(const float* h, const float* W1, const float* b1, const float* W2,
+                         const float* b2, const float* stats, float* out, int B, int R_in, int W_in,
+                         int R_out, int Wp, int C, int HID, int V, fno_stream_t stream);
 int fno_head_bwd_wide_supported(int R_out, int Wp, int C, int HID, int V);
 size_t fno_head_bwd_wide_workspace_bytes(int B, int R_out, int Wp, int C, int V);
 int fno_head_bwd_wide_tc(const float* h, const float* dout, const float* W1, const float* b1,

@@ -302,6 +302,178 @@ head_wide_reduce_kernel(const float* __restrict__ rec, int nrec, float* __restri
 
 constexpr int HW_WG_PARTS = 148;
 
+// ------------------------------------------------------------------------------------------
+// forward for wide trunks (32 < C <= 64):  out = (W2 gelu(W1 h + b1) + b2) * std + mean  per valid pixel.
+// The same (a) GEMM with h through tensor memory; the pre-activation tile is double-buffered so the MMAs of tile i+1
+// run under the GELU epilogue of tile i; the four column quarters of a pixel meet in shared memory (as in head_tc.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int HF_SMEM = 2 * HW_BA_BYTES + 4 * (HW_HID * HW_VP + HW_HID + 2 * 4 * HW_M * HW_VP) + 5 * 8 + 16;
+constexpr unsigned HF_TM_P = 128;         // 2 x 128 columns
+
+struct HfGeo {
+  int W_in, Wp;
+  long npix, plane;
+};
+
+__global__ void __launch_bounds__(HW_THREADS, 1)
+head_fwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ W1, const float* __restrict__ b1,
+                     const float* __restrict__ W2, const float* __restrict__ b2, const float* __restrict__ stats,
+                     float* __restrict__ out, HfGeo g, int C, int V, int tiles_per_sample, int total_tiles, int single) {
+  FNO_SPLIT_CONSTS(single);
+  extern __shared__ __align__(128) unsigned char hsm[];
+  unsigned char* ba_hi = hsm;
+  unsigned char* ba_lo = ba_hi + HW_BA_BYTES;
+  float* W2s = reinterpret_cast<float*>(ba_lo + HW_BA_BYTES);     // [HID][VP]
+  float* b1s = W2s + HW_HID * HW_VP;                              // [HID]
+  float* ox = b1s + HW_HID;                                       // [2 tiles][4 quarters][M][VP]
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(ox + 2 * 4 * HW_M * HW_VP);
+  unsigned long long* h_ready = bars;          // loaders -> MMA
+  unsigned long long* pre_full = bars + 1;     // [2] MMA done
+  unsigned long long* d_free = bars + 3;       // [2] epilogue -> MMA: the pre-activation tile may be overwritten
+  unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
+  if (tid == 0) {
+    mbar_init(h_ready, HW_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(pre_full + s, 1);
+      mbar_init(d_free + s, HW_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == HW_EPI_WARPS) tmem_alloc(tmem_slot, 512);
+  for (int i = tid; i < HW_HID * HW_K; i += HW_THREADS) {
+    const int j = i / HW_K, c = i - j * HW_K;
+    float hi = 0.f, lo = 0.f;
+    if (c < C) split_rm(__ldg(W1 + (size_t)j * C + c), hi, lo, sp_rnd, sp_msk);
+    const int oa = (j & 7) * 16 + (j >> 3) * HW_SBO_A + (c >> 2) * 128 + (c & 3) * 4;
+    *reinterpret_cast<float*>(ba_hi + oa) = hi;
+    *reinterpret_cast<float*>(ba_lo + oa) = lo;
+  }
+  for (int i = tid; i < HW_HID * HW_VP; i += HW_THREADS) {
+    const int j = i / HW_VP, v = i - j * HW_VP;
+    W2s[i] = (v < V) ? __ldg(W2 + (size_t)v * HW_HID + j) : 0.f;
+  }
+  for (int i = tid; i < HW_HID; i += HW_THREADS) b1s[i] = __ldg(b1 + i);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const unsigned tmem_base = *tmem_slot;
+  const int ksteps = (C + 7) / 8;
+  const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == HW_EPI_WARPS) {
+    constexpr unsigned idesc_a = umma_idesc_tf32(HW_M, HW_HID, 0, 0);
+    const unsigned long long d_a_h = umma_desc(ba_hi, 128, HW_SBO_A), d_a_l = umma_desc(ba_lo, 128, HW_SBO_A);
+    for (int it = 0; it < ntl; ++it) {
+      const int st = it & 1;
+      mbar_wait(h_ready, (unsigned)it & 1u);
+      mbar_wait(d_free + st, (((unsigned)it >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      __syncwarp();
+#pragma unroll
+      for (int pass = 0; pass < 3; ++pass)              // lo*hi, hi*lo, hi*hi
+#pragma unroll
+        for (int ks = 0; ks < HW_K / 8; ++ks)
+          if (ks < ksteps && (pass == 2 || !single))
+            tc_mma_tf32_ts_elect(tmem_base + HF_TM_P + (unsigned)(st * HW_HID),
+                                 tmem_base + (pass == 0 ? HW_TM_HLO : HW_TM_HHI) + (unsigned)(8 * ks),
+                                 (pass == 1 ? d_a_l : d_a_h) + (unsigned long long)(ks * (256 >> 4)), idesc_a,
+                                 single ? (unsigned)(ks != 0) : (unsigned)((pass | ks) != 0));
+      tc_commit_elect(pre_full + st);
+    }
+  } else {
+    const int quad = warp & 3, colq = warp >> 2;
+    const int m = quad * 32 + lane;
+    const unsigned tlane = tmem_base + ((unsigned)(quad * 32) << 16);
+    float raw[16];
+    auto load_raw = [&](int it) {                   // channels [16 colq, +16) of pixel m of tile `it`
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const bool inr = it < ntl;
+      const int b = inr ? tile / tiles_per_sample : 0;
+      const long p = inr ? (long)(tile - b * tiles_per_sample) * HW_M + m : 0;
+      const bool valid = inr && p < g.npix;
+      const long r = valid ? p / g.W_in : 0;
+      const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const int c = 16 * colq + e;
+        raw[e] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+      }
+    };
+    auto stage = [&]() {                            // raw -> tensor memory hi / lo, hand over to the MMA warp
+      if (16 * colq < 8 * ksteps) {
+        float hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split_rm(raw[e], hi[e], lo[e], sp_rnd, sp_msk);
+        tmem_st16(tlane + HW_TM_HHI + (unsigned)(16 * colq), hi);
+        if (!single) tmem_st16(tlane + HW_TM_HLO + (unsigned)(16 * colq), lo);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready);
+    };
+    load_raw(0);
+    stage();
+    load_raw(1);
+    for (int it = 0; it < ntl; ++it) {
+      const int st = it & 1;
+      const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+      const int b = tile / tiles_per_sample;
+      const long p0 = (long)(tile - b * tiles_per_sample) * HW_M;
+      mbar_wait(pre_full + st, ((unsigned)it >> 1) & 1u);        // (a) of tile it done: h in tensor memory is free
+      tc_fence_after();
+      if (it + 1 < ntl) stage();                                 // tile it+1's MMAs run under this epilogue
+      load_raw(it + 2);
+      float o[HW_VP];
+#pragma unroll
+      for (int v = 0; v < HW_VP; ++v) o[v] = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[16];
+        tmem_ld16(tlane + HF_TM_P + (unsigned)(st * HW_HID + 32 * colq + 16 * half), v);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const int j = 32 * colq + 16 * half + e;
+          const float gl = gelu_fast(v[e] + b1s[j]);
+          const float4 w2 = *reinterpret_cast<const float4*>(W2s + j * HW_VP);
+          o[0] = fmaf(w2.x, gl, o[0]); o[1] = fmaf(w2.y, gl, o[1]);
+          o[2] = fmaf(w2.z, gl, o[2]); o[3] = fmaf(w2.w, gl, o[3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_free + st);
+      float* oxb = ox + (size_t)st * 4 * HW_M * HW_VP;
+      *reinterpret_cast<float4*>(oxb + (colq * HW_M + m) * HW_VP) = make_float4(o[0], o[1], o[2], o[3]);
+      named_bar_sync(1, HW_EPI_THREADS);
+      if (colq == (it & 3)) {
+        float4 t = *reinterpret_cast<const float4*>(oxb + m * HW_VP);
+#pragma unroll
+        for (int qq = 1; qq < 4; ++qq) {
+          const float4 u = *reinterpret_cast<const float4*>(oxb + (qq * HW_M + m) * HW_VP);
+          t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+        }
+        const long p = p0 + m;
+        if (p < g.npix) {
+          const float of[4] = {t.x, t.y, t.z, t.w};
+          const float* __restrict__ mean = stats + (size_t)b * 2 * V;
+          const float* __restrict__ sd = mean + V;
+          float* __restrict__ op = out + ((size_t)b * g.npix + p) * V;
+#pragma unroll
+          for (int v = 0; v < HW_VP; ++v)
+            if (v < V) op[v] = fmaf(of[v] + __ldg(b2 + v), __ldg(sd + v), __ldg(mean + v));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == HW_EPI_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 }  // namespace fno
 
@@ -368,4 +540,36 @@ extern "C" int fno_head_bwd_wide_tc(const float* h, const float* dout, const flo
   rc = launch_wgrad_tc_rows128(dpre, h, part, B, HW_HID, C, g.plane, HW_WG_PARTS, &nparts, st);
   if (rc != FNO_OK) return rc;
   return launch_wgrad_reduce(part, gW1, gb1, nparts, HW_HID, C, st);
+}
+
+extern "C" int fno_head_fwd_wide_tc(const float* h, const float* W1, const float* b1, const float* W2, const float* b2,
+                                    const float* stats, float* out, int B, int R_in, int W_in, int R_out, int Wp, int C,
+                                    int HID, int V, fno_stream_t stream) {
+  if (!h || !W1 || !b1 || !W2 || !b2 || !stats || !out || B <= 0 || R_in <= 0 || W_in <= 0 || R_out < R_in || Wp < W_in) {
+    set_error("fno_head_fwd_wide_tc: bad argument");
+    return FNO_E_ARG;
+  }
+  if (HID != HW_HID || C < 1 || C > HW_K || V < 1 || V > HW_VP) {
+    set_error("fno_head_fwd_wide_tc: supports hidden width 128, C <= %d, V <= %d (got %d, %d, %d)", HW_K, HW_VP, HID, C, V);
+    return FNO_E_ARG;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  HfGeo g;
+  g.W_in = W_in; g.Wp = Wp;
+  g.npix = (long)R_in * W_in;
+  g.plane = (long)R_out * Wp;
+  const long tps = (g.npix + HW_M - 1) / HW_M;
+  const long total = tps * B;
+  if (total > 0x7fffffffL) { set_error("fno_head_fwd_wide_tc: too many tiles"); return FNO_E_ARG; }
+  static PerDeviceOnce done;
+  if (done.need()) {
+    if (cudaFuncSetAttribute(head_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(head_fwd_wide)");
+    done.mark();
+  }
+  const int ctas = (int)(total < 148 ? total : 148);
+  head_fwd_wide_kernel<<<ctas, HW_THREADS, HF_SMEM, st>>>(h, W1, b1, W2, b2, stats, out, g, C, V, (int)tps, (int)total,
+                                                          g_math_mode.load());
+  count_launch();
+  return check_launch("head_fwd_wide_kernel");
 }

@@ -91,6 +91,7 @@ def load():
             "fno_head_bwd_workspace_bytes": (C.c_size_t, [i, i, i]),
             "fno_head_bwd": (i, [vp] * 12 + [i] * 8 + [vp]),
             "fno_head_bwd_tc": (i, [vp] * 12 + [i] * 8 + [vp]),
+            "fno_head_fwd_wide_tc": (i, [vp] * 7 + [i] * 8 + [vp]),
             "fno_head_bwd_wide_supported": (i, [i, i, i, i, i]),
             "fno_head_bwd_wide_workspace_bytes": (C.c_size_t, [i, i, i, i, i]),
             "fno_head_bwd_wide_tc": (i, [vp] * 12 + [i] * 8 + [vp]),
@@ -124,7 +125,7 @@ EXPORTED_SYMBOLS = (
     "fno_pointwise_wgrad_workspace_bytes", "fno_pointwise_wgrad", "fno_pointwise_bwd",
     "fno_lift_stats_workspace_bytes", "fno_lift_stats", "fno_lift_fwd", "fno_lift_bwd_workspace_bytes",
     "fno_lift_bwd", "fno_head_fwd", "fno_head_fwd_tc", "fno_head_bwd_workspace_bytes", "fno_head_bwd", "fno_head_bwd_tc",
-    "fno_head_bwd_wide_supported", "fno_head_bwd_wide_workspace_bytes", "fno_head_bwd_wide_tc",
+    "fno_head_fwd_wide_tc", "fno_head_bwd_wide_supported", "fno_head_bwd_wide_workspace_bytes", "fno_head_bwd_wide_tc",
     "fno_nrmse_workspace_bytes", "fno_nrmse_fwd", "fno_nrmse_bwd", "fno_opt_chunk_floats",
     "fno_opt_chunk_bytes", "fno_clip_adam_step",
     "fno_metric_workspace_bytes", "fno_metric_func", "fno_window_shift",
@@ -580,6 +581,12 @@ def head_fwd(geo: TrunkGeo, h, W1, b1, W2, b2, stats) -> torch.Tensor:
         _check(load().fno_head_fwd_tc(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                       stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
                "fno_head_fwd_tc")
+        return out
+    if HEAD_TC and HID == 128 and C <= 64 and V <= 4:
+        # wide trunks (cfg 3): h through tensor memory as the A operand (head_wide_tc.cu)
+        _check(load().fno_head_fwd_wide_tc(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
+                                           stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()),
+               "fno_head_fwd_wide_tc")
         return out
     _check(load().fno_head_fwd(h.data_ptr(), W1.data_ptr(), b1.data_ptr(), W2.data_ptr(), b2.data_ptr(),
                                stats.data_ptr(), out.data_ptr(), B, *geo.ints, C, HID, V, _stream()), "fno_head_fwd")
