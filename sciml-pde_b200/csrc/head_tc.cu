@@ -151,14 +151,16 @@ head_fwd_tc_kernel(const float* __restrict__ h, const float* __restrict__ W1, co
       const long p = in ? (long)(tile - b * tiles_per_sample) * TC_M + pm : 0;
       const bool valid = in && p < g.npix;
       const long r = valid ? p / g.W_in : 0;
-      const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+      // running pointer over this thread's channels 4 kq + 16 u + e (two adds per access instead of a rebuilt 64-bit index)
+      const float* hp = h + ((size_t)b * C + 4 * kq) * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+      const int cmax = valid ? C - 4 * kq : 0;
+      const int pl = (int)g.plane;
 #pragma unroll
       for (int u = 0; u < TCF_MAXCH; ++u) {
-        const int kc = kq + 4 * u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int c = 4 * kc + e;
-          raw[u][e] = (valid && kc < 2 * ksteps && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+          raw[u][e] = (16 * u + e < cmax) ? __ldg(hp) : 0.f;
+          hp += (e < 3) ? pl : 13 * pl;
         }
       }
     };
@@ -280,7 +282,7 @@ extern "C" int fno_head_fwd_tc(const float* h, const float* W1, const float* b1,
   g.plane = (long)R_out * Wp;
   const long tps = (g.npix + TC_M - 1) / TC_M;
   const long total = tps * B;
-  if (total > 0x7fffffffL) { set_error("fno_head_fwd_tc: too many tiles"); return FNO_E_ARG; }
+  if (total > 0x7fffffffL || g.plane > 0x7fffffffL / 16) { set_error("fno_head_fwd_tc: too many tiles / plane too large"); return FNO_E_ARG; }
   const size_t smem = 4 * A_BYTES + 2 * B_BYTES + sizeof(float) * (TC_HID * TC_VP + TC_HID + 8 * TC_M * TC_VP) +
                       6 * sizeof(unsigned long long) + 16;
   static PerDeviceOnce done;

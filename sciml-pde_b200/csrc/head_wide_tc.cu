@@ -114,6 +114,7 @@ head_bwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ dout
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
   const int ksteps = (C + 7) / 8;
+  const int Pl = (int)g.plane;              // 32-bit element offsets (the launcher checks 128 plane < 2^31)
   const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
 
   if (warp == HW_EPI_WARPS) {
@@ -164,11 +165,12 @@ head_bwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ dout
       const int b = inr ? tile / tiles_per_sample : 0;
       const long q = inr ? (long)(tile - b * tiles_per_sample) * HW_M + m : 0;
       const bool inplane = inr && q < g.plane;
-      const float* __restrict__ hp = h + (size_t)b * C * g.plane + (inplane ? q : 0);
+      const float* hp = h + ((size_t)b * C + 16 * colq) * g.plane + (inplane ? q : 0);   // running pointer: 2 adds per access
+      const int cmax = inplane ? C - 16 * colq : 0;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int c = 16 * colq + e;
-        raw[e] = (inplane && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+        raw[e] = (e < cmax) ? __ldg(hp) : 0.f;
+        hp += Pl;
       }
     };
     load_raw(0);
@@ -209,7 +211,7 @@ head_bwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ dout
       mbar_wait(pre_full, ph);
       tc_fence_after();
       float act[32];
-      float* __restrict__ dg = dpre_g + ((size_t)b * HW_HID + 32 * colq) * g.plane + q;
+      float* dg = dpre_g + ((size_t)b * HW_HID + 32 * colq) * g.plane + q;     // running pointer over the hidden units
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         float v[16], hi[16], lo[16];
@@ -224,7 +226,8 @@ head_bwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ dout
           const float dact = fmaf(w2.x, dy[0], fmaf(w2.y, dy[1], fmaf(w2.z, dy[2], w2.w * dy[3])));
           const float dpre = dact * gp;
           act[16 * half + e] = gl;
-          if (inplane) dg[(size_t)(16 * half + e) * g.plane] = dpre;
+          if (inplane) *dg = dpre;
+          dg += Pl;
           split_rm(dpre, hi[e], lo[e], sp_rnd, sp_msk);
         }
         tmem_st16(tlane + col, hi);
@@ -251,10 +254,13 @@ head_bwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ dout
         float v[16];
         tmem_ld16(tlane + HW_TM_DH + (unsigned)(16 * colq), v);
         if (inplane) {
-          float* __restrict__ dp = dh + ((size_t)b * C + 16 * colq) * g.plane + q;
+          float* dp = dh + ((size_t)b * C + 16 * colq) * g.plane + q;
+          const int nc = C - 16 * colq;
 #pragma unroll
-          for (int e = 0; e < 16; ++e)
-            if (16 * colq + e < C) dp[(size_t)e * g.plane] = valid ? v[e] : 0.f;
+          for (int e = 0; e < 16; ++e) {
+            if (e < nc) *dp = valid ? v[e] : 0.f;
+            dp += Pl;
+          }
         }
       }
       tc_fence_before();
@@ -361,6 +367,7 @@ head_fwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ W1, 
   tc_fence_after();
   const unsigned tmem_base = *tmem_slot;
   const int ksteps = (C + 7) / 8;
+  const int Pl = (int)g.plane;
   const int ntl = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
   if (warp == HW_EPI_WARPS) {
@@ -395,11 +402,12 @@ head_fwd_wide_kernel(const float* __restrict__ h, const float* __restrict__ W1, 
       const long p = inr ? (long)(tile - b * tiles_per_sample) * HW_M + m : 0;
       const bool valid = inr && p < g.npix;
       const long r = valid ? p / g.W_in : 0;
-      const float* __restrict__ hp = h + (size_t)b * C * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+      const float* hp = h + ((size_t)b * C + 16 * colq) * g.plane + r * g.Wp + (valid ? p - r * g.W_in : 0);
+      const int cmax = valid ? C - 16 * colq : 0;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
-        const int c = 16 * colq + e;
-        raw[e] = (valid && c < C) ? __ldg(hp + (size_t)c * g.plane) : 0.f;
+        raw[e] = (e < cmax) ? __ldg(hp) : 0.f;
+        hp += Pl;
       }
     };
     auto stage = [&]() {                            // raw -> tensor memory hi / lo, hand over to the MMA warp
@@ -515,7 +523,7 @@ extern "C" int fno_head_bwd_wide_tc(const float* h, const float* dout, const flo
   g.plane = (long)R_out * Wp;
   const long tps = (g.plane + HW_M - 1) / HW_M;
   const long total = tps * B;
-  if (total > 0x7fffffffL) { set_error("fno_head_bwd_wide_tc: too many tiles"); return FNO_E_ARG; }
+  if (total > 0x7fffffffL || g.plane > 0x7fffffffL / 128) { set_error("fno_head_bwd_wide_tc: too many tiles / plane too large"); return FNO_E_ARG; }
   static PerDeviceOnce done;
   if (done.need()) {
     if (cudaFuncSetAttribute(head_bwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_SMEM) != cudaSuccess)
@@ -560,7 +568,7 @@ extern "C" int fno_head_fwd_wide_tc(const float* h, const float* W1, const float
   g.plane = (long)R_out * Wp;
   const long tps = (g.npix + HW_M - 1) / HW_M;
   const long total = tps * B;
-  if (total > 0x7fffffffL) { set_error("fno_head_fwd_wide_tc: too many tiles"); return FNO_E_ARG; }
+  if (total > 0x7fffffffL || g.plane > 0x7fffffffL / 128) { set_error("fno_head_fwd_wide_tc: too many tiles / plane too large"); return FNO_E_ARG; }
   static PerDeviceOnce done;
   if (done.need()) {
     if (cudaFuncSetAttribute(head_fwd_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM) != cudaSuccess)

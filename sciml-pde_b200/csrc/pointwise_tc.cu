@@ -111,20 +111,25 @@ pointwise_tc_kernel(const float* __restrict__ in, const float* __restrict__ W, c
     const int kq = tid >> 7;                       // chunk residue staged by this thread
     const int abase = (pm & 7) * 16 + (pm >> 3) * PT_SBO;
     float raw[PT_MAXCH][4];
+    // 32-bit element offsets (the launcher checks 64 N < 2^31): one IMAD per access instead of a 64-bit product -- the
+    // first version spent 55 % of its issue slots on address arithmetic (profiles/r2c_wide_ncu.md)
+    const int Ni = (int)N;
     auto load_raw = [&](int it) {                  // this thread's channels of tile `it` (zeros past the end)
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const bool inr = it < ntl;
       const int b = inr ? tile / tiles_per_sample : 0;
-      const long p = inr ? (long)(tile - b * tiles_per_sample) * PT_M + pm : 0;
-      const bool valid = inr && p < N;
-      const float* __restrict__ ip = in + (size_t)b * Cin * N + (valid ? p : 0);
+      const int p = inr ? (tile - b * tiles_per_sample) * PT_M + pm : 0;
+      const bool valid = inr && p < Ni;
+      // a running pointer (two adds per access): the compiler otherwise rebuilds base + index * stride from the constant
+      // bank for every element (8 integer instructions per load)
+      const float* ip = in + ((size_t)b * Cin + 4 * kq) * N + (valid ? p : 0);
+      const int cmax = valid ? Cin - 4 * kq : 0;   // channels 4 kq + j, j < cmax, exist
 #pragma unroll
       for (int u = 0; u < PT_MAXCH; ++u) {
-        const int kc = kq + 4 * u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int c = 4 * kc + e;
-          raw[u][e] = (valid && c < Cin) ? __ldg(ip + (size_t)c * N) : 0.f;
+          raw[u][e] = (16 * u + e < cmax) ? __ldg(ip) : 0.f;
+          ip += (e < 3) ? Ni : 13 * Ni;
         }
       }
     };
@@ -153,7 +158,7 @@ pointwise_tc_kernel(const float* __restrict__ in, const float* __restrict__ W, c
       const unsigned ph = (unsigned)(it >> 1) & 1u;
       const int tile = (int)blockIdx.x + it * (int)gridDim.x;
       const int b = tile / tiles_per_sample;
-      const long p = (long)(tile - b * tiles_per_sample) * PT_M + m;
+      const int p = (tile - b * tiles_per_sample) * PT_M + m;
       // stage tile it+1 (its operand buffer was last read by the MMAs of tile it-1, whose completion this thread
       // observed in the previous epilogue), then put tile it+2's loads in flight
       if (it + 1 < ntl) store_raw(st ^ 1);
@@ -166,11 +171,14 @@ pointwise_tc_kernel(const float* __restrict__ in, const float* __restrict__ W, c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_free + st);     // the accumulator may be overwritten by tile it+2's MMAs
-      if (p < N) {
-        float* __restrict__ op = out + ((size_t)b * Cout + colq * 16) * N + p;
+      if (p < Ni) {
+        float* op = out + ((size_t)b * Cout + colq * 16) * N + p;
+        const int nout = Cout - colq * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (colq * 16 + i < Cout) op[(size_t)i * N] = v[i] + bs[colq * 16 + i];
+        for (int i = 0; i < 16; ++i) {
+          if (i < nout) *op = v[i] + bs[colq * 16 + i];
+          op += Ni;
+        }
       }
     }
   }
@@ -389,7 +397,7 @@ int launch_pointwise_tc(const float* in, const float* W, const float* bias, floa
   const int Cout = transpose ? Ci : Co, Cin = transpose ? Co : Ci;
   const long tps = (N + PT_M - 1) / PT_M;
   const long total = tps * B;
-  if (total > 0x7fffffffL) { set_error("fno_pointwise_fwd: too many tiles"); return FNO_E_ARG; }
+  if (total > 0x7fffffffL || N > 0x7fffffffL / 64) { set_error("fno_pointwise_fwd: too many tiles / plane too large"); return FNO_E_ARG; }
   static PerDeviceOnce done;
   if (done.need()) {
     if (cudaFuncSetAttribute(pointwise_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM) != cudaSuccess)
@@ -422,7 +430,7 @@ static int launch_wgrad_tc_t(const float* ds, const float* a, float* part, int B
   const long spc = (total + ctas - 1) / ctas;
   ctas = (total + spc - 1) / spc;
   wgrad_tc_kernel<RA, KT><<<(unsigned)ctas, WT_THREADS, Cfg::SMEM, st>>>(ds, a, part, Co, Ci, N, sps, total, spc,
-                                                                        g_math_mode.load());
+                                                                                g_math_mode.load());
   count_launch();
   *nparts = (int)ctas;
   return check_launch("wgrad_tc_kernel");

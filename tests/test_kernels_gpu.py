@@ -251,6 +251,34 @@ def test_mix_tensor_core(lib, B, Ci, Co, spatial, modes, tc):
 
 
 @pytest.mark.parametrize("low", ["tf32", "bf16"])
+def test_pointwise_tensor_core_math_modes(lib, low):
+    """The width-64 bypass kernels (pointwise_tc.cu: product, data gradient, weight gradient) follow the math mode."""
+    rng = np.random.default_rng(3)
+    B, C, spatial = 2, 64, (66, 66)
+    a = rng.standard_normal((B, C) + spatial).astype(np.float32)
+    w = rng.standard_normal((C, C, 1, 1)).astype(np.float32) / 8
+    b = rng.standard_normal(C).astype(np.float32)
+    ds = rng.standard_normal((B, C) + spatial).astype(np.float32)
+    w2 = w.reshape(C, C).astype(np.float64)
+    refs = (O.pointwise_conv(a, w, b), np.einsum("oi,bo...->bi...", w2, ds.astype(np.float64)),
+            np.einsum("bop,bip->oi", ds.reshape(B, C, -1).astype(np.float64), a.reshape(B, C, -1).astype(np.float64)))
+    errs = {}
+    for mode in (low, "fp32"):
+        prev = lib.set_math_mode(mode)
+        try:
+            out = lib.pointwise_fwd(dev(a), dev(w), dev(b))
+            back = lib.pointwise_fwd(dev(ds), dev(w), None, transpose=True)
+            gw, _ = lib.pointwise_wgrad(dev(ds), dev(a), w.shape)
+            torch.cuda.synchronize()
+        finally:
+            lib.set_math_mode(prev)
+        errs[mode] = [O.rel_err(t.cpu().numpy().reshape(r.shape), r) for t, r in zip((out, back, gw), refs)]
+    assert max(errs["fp32"]) < TOL, errs
+    assert max(errs[low]) < MODE_TOL[low], errs
+    assert min(errs[low]) > 4 * max(errs["fp32"]), errs
+
+
+@pytest.mark.parametrize("low", ["tf32", "bf16"])
 def test_mix_tensor_core_math_modes(lib, low):
     """tf32 / bf16 modes reach K2's tensor-core kernels: single pass, stated bounds 2e-3 / 2e-2, visibly worse than fp32."""
     rng = np.random.default_rng(5)
@@ -560,7 +588,8 @@ MODE_TOL = {"tf32": TF32_TOL, "bf16": BF16_TOL}
 
 
 @pytest.mark.parametrize("low", ["tf32", "bf16"])
-@pytest.mark.parametrize("spatial,C,V,B", [((64, 64), 20, 2, 3), ((40, 50), 23, 4, 2)])
+@pytest.mark.parametrize("spatial,C,V,B", [((64, 64), 20, 2, 3), ((40, 50), 23, 4, 2),
+                                           ((62, 62), 64, 3, 2)])        # wide trunk: head_wide_tc.cu kernels
 def test_head_tf32_mode(lib, spatial, C, V, B, low):
     from fno_b200 import ops
     from oracle import fno_port as P
