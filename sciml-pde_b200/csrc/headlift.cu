@@ -146,6 +146,7 @@ lift_fwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
   const long p = (long)blockIdx.x * LIFT_THREADS + threadIdx.x;
   const bool active = p < g.npix;
   const float* __restrict__ xp = x + ((size_t)b * g.npix + (active ? p : 0)) * F1;
+  const bool vec4 = (F1 % 4 == 0) && ((reinterpret_cast<size_t>(x) & 15u) == 0);
   const float* __restrict__ gp = grid + ((size_t)b * g.npix + (active ? p : 0)) * G;
   const long off = active ? pix_offset(g, p) : 0;
   float mu[VMAX], rs[VMAX];
@@ -168,14 +169,31 @@ lift_fwd_kernel(const float* __restrict__ x, const float* __restrict__ grid, con
 #pragma unroll
     for (int cc = 0; cc < CT; ++cc) acc[cc] = bs[cc];
     // normalised history (x - mean_v) / std_v, feature index f = t * V + v   (fno.py:143-149)
-    for (int t = 0; t < T; ++t) {
+    if (vec4 && (V == 2 || V == 4)) {
+      // a pixel's T * V history values are contiguous: 16-byte loads (a warp's scalar loads at an 80-byte lane stride
+      // cost 20 L1 wavefronts per instruction -- the kernel was bound by them, not by HBM or the FMAs)
+      for (int f4 = 0; f4 < F1; f4 += 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(xp + f4));
+        const float xv[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int v = 0; v < VMAX; ++v) {
-        if (v < V) {
-          const float xn = (__ldg(xp + t * V + v) - mu[v]) * rs[v];
-          const float* wr = ws + (t * V + v) * CT;
+        for (int j = 0; j < 4; ++j) {
+          const int v = V == 2 ? (j & 1) : j;                       // (f4 + j) % V for V = 2 / 4
+          const float xn = (xv[j] - mu[v]) * rs[v];
+          const float* wr = ws + (f4 + j) * CT;
 #pragma unroll
           for (int cc = 0; cc < CT; ++cc) acc[cc] = fmaf(wr[cc], xn, acc[cc]);
+        }
+      }
+    } else {
+      for (int t = 0; t < T; ++t) {
+#pragma unroll
+        for (int v = 0; v < VMAX; ++v) {
+          if (v < V) {
+            const float xn = (__ldg(xp + t * V + v) - mu[v]) * rs[v];
+            const float* wr = ws + (t * V + v) * CT;
+#pragma unroll
+            for (int cc = 0; cc < CT; ++cc) acc[cc] = fmaf(wr[cc], xn, acc[cc]);
+          }
         }
       }
     }
