@@ -9,6 +9,11 @@
 //     huge K = B*N and a tiny output, so it is a split-K reduction: a CTA stages a K-slab of both
 //     operands in shared memory, each warp owns a T x T output tile with lanes striding K, and
 //     per-CTA partials are combined by a second fixed-order pass (deterministic, no atomics).
+#include <cuda.h>
+
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace fno {
@@ -298,26 +303,73 @@ constexpr int WG2_STAGES = 2;
 constexpr int WG2_KT = 512;      // pixels per slab: 2 KB per bulk copy (the TMA unit retires ~1 copy / 46 cycles / SM,
                                  // so 512-byte copies cap the stream at ~3 TB/s -- profiles/r1_d)
 constexpr int WG2_MAXW = 8;      // consumer warps per CTA
+// TMAP: a slab is TWO 2-D tensor-map copies -- box {512 pixels, C planes} of the [planes][pixels] view of ds and of a, with
+// the row taken as 8-byte elements (PAIRS) so that 512 pixels fit the 256-element box limit: 40 KB per copy at width 20
+// instead of Co + Ci bulk copies of 2 KB.  Pixels past the end of a sample are zero-filled by the TMA unit (and still counted by
+// complete_tx).  Measured at cfg 1 (B = 128, profiles/r2g_wgrad_forms.md): bulk copies 124 us, the same ring fed by tensor
+// maps 93 us, + FULL 89 us; a kernel that only waits for its slabs 79-85 us in every form (the TMA feed tops out at ~4.5 TB/s),
+// and every bulk copy costs ~40 ns of issue on top (256-pixel slabs with twice the copies: 171 us).
+__device__ __forceinline__ void wg2_tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ---- tensor maps of the operand feed (driver entry point resolved through the runtime: no link-time libcuda dependency) ----
+typedef CUresult (*Wg2EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+Wg2EncodeTiledFn wg2_encode_fn() {
+  static Wg2EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<Wg2EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// [planes][pixels] f32 view of a channel-first tensor, box {kt pixels, c planes}, zero fill outside
+bool wg2_make_map(CUtensorMap* m, const float* base, unsigned long long pixels, unsigned long long planes, unsigned kt, unsigned c) {
+  Wg2EncodeTiledFn fn = wg2_encode_fn();
+  if (fn == nullptr || base == nullptr || c == 0 || c > 256 || kt > 512 || (pixels & 1ull)) return false;
+  const cuuint64_t gdim[2] = {pixels / 2, planes};
+  const cuuint64_t gstr[1] = {pixels * 4ull};
+  const cuuint32_t box[2] = {kt / 2, c};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool wg2_use_maps() {
+  static const bool on = [] { const char* e = std::getenv("FNO_WG2"); return !(e != nullptr && e[0] == '0'); }();
+  return on && wg2_encode_fn() != nullptr;
+}
 
 // DGRAD: the same pass also produces the bypass data gradient dx[b, i, p] = sum_o W[o, i] ds[b, o, p]
 // (autograd of nn.Conv2d(C, C, 1), fno/fno.py:162) from the ds slab that is already in shared memory --
 // one read of the ds tensor per layer instead of two.  Thread = two adjacent pixels of the 512-pixel slab
 // (8 consumer warps), all Ci outputs in registers, weight rows broadcast with LDS.128.
-template <int T, bool DGRAD>
+template <int T, bool DGRAD, int KT2 = WG2_KT, int NST = WG2_STAGES, bool TMAP = false, bool PAIRS = false, bool FULL = false>
 __global__ void __launch_bounds__(32 * WG2_MAXW)
 wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a, float* __restrict__ part, int Co,
                       int Ci, long N, int slabs_per_sample, long total_slabs, long slabs_per_cta, int tiles_i,
-                      int ntiles, int nwarps, int KH, const float* __restrict__ Wm, float* __restrict__ dx) {
-  extern __shared__ __align__(16) float sm[];   // WG2_STAGES x ([Co][KT] ds slab, [Ci][KT] a slab), then barriers
-  constexpr int KT2 = WG2_KT;
+                      int ntiles, int nwarps, int KH, const float* __restrict__ Wm, float* __restrict__ dx,
+                      const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_a) {
+  static_assert(!DGRAD || KT2 == WG2_KT, "the fused data gradient covers a 512-pixel slab with 256 threads");
+  constexpr bool EARLY_REFILL = NST > 2;
+  extern __shared__ __align__(128) float wg2_sm[];  // NST x ([Co][KT2] ds slab, [Ci][KT2] a slab), then barriers
+  float* const sm = wg2_sm;
   const int rows = Co + Ci;
-  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)WG2_STAGES * rows * KT2);
-  unsigned long long* empty = full + WG2_STAGES;
-  float* ws = reinterpret_cast<float*>(empty + WG2_STAGES);     // DGRAD: W [Co][2T] (rows zero-padded)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(sm + (size_t)NST * rows * KT2);
+  unsigned long long* empty = full + NST;
+  float* ws = reinterpret_cast<float*>(empty + NST);            // DGRAD: W [Co][2T] (rows zero-padded)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG2_STAGES; ++s) {
+    for (int s = 0; s < NST; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, nwarps);
     }
@@ -340,14 +392,24 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
   auto produce = [&](long slab) {
     if (slab >= s_end) return;
     const int it = (int)(slab - s_begin);
-    const int stage = it % WG2_STAGES;
-    const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
+    const int stage = it % NST;
+    const unsigned ph = (unsigned)(it / NST) & 1u;
     mbar_wait(empty + stage, ph ^ 1u);            // every consumer warp is done with the slab that used this stage
     const long b = slab / slabs_per_sample;
     const long k0 = (slab - b * slabs_per_sample) * KT2;
+    float* dst = sm + (size_t)stage * rows * KT2;
+    if (TMAP) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(full + stage, (unsigned)(KT2 * sizeof(float)) * (unsigned)rows);   // whole boxes, zero fill included
+        const int c0 = PAIRS ? (int)(k0 >> 1) : (int)k0;
+        wg2_tma_load_2d(dst, &tm_ds, c0, (int)(b * Co), full + stage);
+        wg2_tma_load_2d(dst + (size_t)Co * KT2, &tm_a, c0, (int)(b * Ci), full + stage);
+      }
+      __syncwarp();
+      return;
+    }
     const long left = N - k0;
     const unsigned bytes = (unsigned)((left < KT2 ? left : KT2) * sizeof(float));
-    float* dst = sm + (size_t)stage * rows * KT2;
     if (lane == 0) mbar_arrive_expect_tx(full + stage, bytes * (unsigned)rows);
     __syncwarp();
     for (int c = lane; c < rows; c += 32) {
@@ -356,7 +418,7 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
     }
   };
   if (warp == 0) {
-    for (int s = 0; s < WG2_STAGES; ++s) produce(s_begin + s);
+    for (int s = 0; s < NST; ++s) produce(s_begin + s);
   }
 
   // ---- consumer warps: (tile, pixel part) each; a tile is a T x T block of outputs ------------
@@ -365,7 +427,12 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
   const bool has_tile = tile < ntiles;
   const int to = has_tile ? (tile / tiles_i) * T : 0;
   const int ti = has_tile ? (tile % tiles_i) * T : 0;
-  const bool bias_tile = has_tile && (ti == 0);
+  // FULL (every tile complete, two tiles per tile row): no bounds predicates, operand addresses are one base register plus
+  // immediates, and the two warps of a tile row share the bias rows (T/2 each) so that all warps carry the same work
+  const bool bias_hi = FULL && ti != 0;
+  const bool bias_tile = has_tile && (FULL || ti == 0);
+  const float* const ds_t = sm + (size_t)to * KT2 + 4 * lane;
+  const float* const a_t = sm + (size_t)(Co + ti) * KT2 + 4 * lane;
   float acc[T][T];
   float accb[T];
 #pragma unroll
@@ -377,8 +444,10 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
   const int steps = KT2 / 128;                    // 128 pixels (32 lanes x 4) per step
   for (long slab = s_begin; slab < s_end; ++slab) {
     const int it = (int)(slab - s_begin);
-    const int stage = it % WG2_STAGES;
-    const unsigned ph = (unsigned)(it / WG2_STAGES) & 1u;
+    const int stage = it % NST;
+    const unsigned ph = (unsigned)(it / NST) & 1u;
+    // deep ring: refill the stage of the PREVIOUS slab now (the other warps left it a whole slab of products ago)
+    if (EARLY_REFILL && warp == 0 && it > 0) produce(slab - 1 + NST);
     mbar_wait(full + stage, ph);
     const long b = slab / slabs_per_sample;
     const long left = N - (slab - b * slabs_per_sample) * KT2;
@@ -388,18 +457,30 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
         if (px >= left) break;
         const float* ds_s = sm + (size_t)stage * rows * KT2 + px;
         const float* a_s = ds_s + (size_t)Co * KT2;
+        const int soff = stage * rows * KT2 + st * 128;
         float4 dv[T];
 #pragma unroll
-        for (int r = 0; r < T; ++r)
-          dv[r] = (to + r < Co) ? *reinterpret_cast<const float4*>(ds_s + (to + r) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bias_tile) {
+        for (int r = 0; r < T; ++r) {
+          if (FULL) dv[r] = *reinterpret_cast<const float4*>(ds_t + soff + r * KT2);
+          else dv[r] = (to + r < Co) ? *reinterpret_cast<const float4*>(ds_s + (to + r) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (FULL) {
+          if (!bias_hi) {
+#pragma unroll
+            for (int r = 0; r < T / 2; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
+          } else {
+#pragma unroll
+            for (int r = T / 2; r < T; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
+          }
+        } else if (bias_tile) {
 #pragma unroll
           for (int r = 0; r < T; ++r) accb[r] += (dv[r].x + dv[r].y) + (dv[r].z + dv[r].w);
         }
 #pragma unroll
         for (int c = 0; c < T; ++c) {
-          const float4 av =
-              (ti + c < Ci) ? *reinterpret_cast<const float4*>(a_s + (ti + c) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 av;
+          if (FULL) av = *reinterpret_cast<const float4*>(a_t + soff + c * KT2);
+          else av = (ti + c < Ci) ? *reinterpret_cast<const float4*>(a_s + (ti + c) * KT2) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
           for (int r = 0; r < T; ++r) {
             acc[r][c] = fmaf(dv[r].x, av.x, acc[r][c]);
@@ -438,7 +519,7 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(empty + stage);
-    if (warp == 0) produce(slab + WG2_STAGES);    // refill the stage just released (waits for the other warps)
+    if (!EARLY_REFILL && warp == 0) produce(slab + NST);    // refill the stage just released (waits for the other warps)
   }
   if (!has_tile) return;
   // part[(cta * KH + kh)][Co][Ci + 1]
@@ -452,13 +533,36 @@ wgrad2_partial_kernel(const float* __restrict__ ds, const float* __restrict__ a,
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (lane == 0 && to + r < Co && ti + c < Ci) pp[(size_t)(to + r) * (Ci + 1) + ti + c] = v;
     }
-    if (bias_tile) {
+    if (bias_tile && (!FULL || ((r >= T / 2) == bias_hi))) {
       float v = accb[r];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (lane == 0 && to + r < Co) pp[(size_t)(to + r) * (Ci + 1) + Ci] = v;
     }
   }
+}
+
+// One place that names every instantiation of the TMA-fed kernel: attr_only sets the shared-memory attribute of all of them
+// (once per device), otherwise the one selected by (dgrad, maps, full) is launched.
+template <int T, bool DGRAD, bool TMAP, bool FULL, typename... Args>
+void wg2_launch_one(bool attr_only, dim3 grid, int threads, size_t smem, cudaStream_t st, int& rc, Args... args) {
+  auto kern = wgrad2_partial_kernel<T, DGRAD, WG2_KT, WG2_STAGES, TMAP, TMAP, FULL>;
+  if (attr_only) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      rc = check_launch("cudaFuncSetAttribute(wgrad2)");
+    return;
+  }
+  kern<<<grid, threads, smem, st>>>(args...);
+}
+template <int T, typename... Args>
+void wg2_launch(bool attr_only, bool dgrad, bool maps, bool full, dim3 grid, int threads, size_t smem, cudaStream_t st, int& rc,
+                Args... args) {
+  if (attr_only || (dgrad && maps && full)) wg2_launch_one<T, true, true, true>(attr_only, grid, threads, smem, st, rc, args...);
+  if (attr_only || (dgrad && maps && !full)) wg2_launch_one<T, true, true, false>(attr_only, grid, threads, smem, st, rc, args...);
+  if (attr_only || (dgrad && !maps)) wg2_launch_one<T, true, false, false>(attr_only, grid, threads, smem, st, rc, args...);
+  if (attr_only || (!dgrad && maps && full)) wg2_launch_one<T, false, true, true>(attr_only, grid, threads, smem, st, rc, args...);
+  if (attr_only || (!dgrad && maps && !full)) wg2_launch_one<T, false, true, false>(attr_only, grid, threads, smem, st, rc, args...);
+  if (attr_only || (!dgrad && !maps)) wg2_launch_one<T, false, false, false>(attr_only, grid, threads, smem, st, rc, args...);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -680,15 +784,6 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
   // v2 (TMA bulk-fed): persistent CTAs, one per SM, each over a contiguous range of 512-pixel slabs
   const size_t smem2 = sizeof(float) * (size_t)WG2_STAGES * (Co + Ci) * WG2_KT + 2 * WG2_STAGES * sizeof(unsigned long long);
   if (aligned && smem2 <= 200 * 1024 && ntiles <= WG2_MAXW) {
-    static PerDeviceOnce attr2_done;
-    if (attr2_done.need()) {
-      if (cudaFuncSetAttribute(wgrad2_partial_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-              cudaSuccess ||
-          cudaFuncSetAttribute(wgrad2_partial_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) !=
-              cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(wgrad2)");
-      attr2_done.mark();
-    }
     const int KH = (2 * ntiles <= WG2_MAXW) ? 2 : 1;       // pixel halves per tile
     const int warps2 = ntiles * KH;
     const int sps2 = (int)((N + WG2_KT - 1) / WG2_KT);
@@ -700,18 +795,33 @@ static int pointwise_wgrad_impl(const float* ds, const float* a, float* gW, floa
     const size_t smem2d = smem2 + sizeof(float) * (size_t)Co * 2 * T;
     const bool dgrad = Wm != nullptr && dx != nullptr && warps2 == WG2_MAXW && Co <= 2 * T && Ci <= 2 * T &&
                        smem2d <= 200 * 1024 && (reinterpret_cast<size_t>(dx) % 8) == 0;
-    if (dgrad)
-      wgrad2_partial_kernel<T, true><<<dim3((unsigned)ctas2, 1), 32 * warps2, smem2d, st>>>(
-          ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH, Wm, dx);
-    else
-      wgrad2_partial_kernel<T, false><<<dim3((unsigned)ctas2, 1), 32 * warps2, smem2, st>>>(
-          ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH, nullptr, nullptr);
+    // operand feed: two 2-D tensor-map copies per slab (box {512 pixels as 256 8-byte elements, C planes} of ds and of a)
+    // when the driver entry point is there, else one bulk copy per channel row (FNO_WG2=0 forces the latter)
+    CUtensorMap mds, ma;
+    memset(&mds, 0, sizeof(mds)); memset(&ma, 0, sizeof(ma));
+    const bool use_map = wg2_use_maps() && N < (1L << 31) && (long)B * (Co > Ci ? Co : Ci) < (1L << 31) &&
+                         wg2_make_map(&mds, ds, (unsigned long long)N, (unsigned long long)B * Co, WG2_KT, Co) &&
+                         wg2_make_map(&ma, a, (unsigned long long)N, (unsigned long long)B * Ci, WG2_KT, Ci);
+    const bool full = use_map && (T % 2 == 0) && tiles_i == 2 && Ci == 2 * T && Co % T == 0;
+    static PerDeviceOnce attr2_done;
+    if (attr2_done.need()) {
+      int rca = FNO_OK;
+      wg2_launch<T>(true, true, true, true, dim3(1), 0, 0, st, rca, ds, a, part, Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles,
+                    warps2, KH, Wm, dx, mds, ma);
+      if (rca != FNO_OK) return rca;
+      attr2_done.mark();
+    }
+    int rcl = FNO_OK;
+    wg2_launch<T>(false, dgrad, use_map, full, dim3((unsigned)ctas2, 1), 32 * warps2, dgrad ? smem2d : smem2, st, rcl, ds, a, part,
+                  Co, Ci, N, sps2, total2s, spc2, tiles_i, ntiles, warps2, KH, dgrad ? Wm : nullptr, dgrad ? dx : nullptr, mds, ma);
+    if (rcl != FNO_OK) return rcl;
+    const long nparts2 = ctas2 * KH;
     if (dgrad && fused) *fused = 1;
     count_launch();
     int rc2 = check_launch("wgrad2_partial_kernel");
     if (rc2 != FNO_OK) return rc2;
     const int total2 = Co * (Ci + 1);
-    wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)ctas2 * KH, Co, Ci);
+    wgrad_reduce_kernel<<<(total2 * 32 + 127) / 128, 128, 0, st>>>(part, gW, gb, (int)nparts2, Co, Ci);
     count_launch();
     return check_launch("wgrad_reduce_kernel");
   }
