@@ -85,6 +85,70 @@ lift_stats_partial_kernel(const float* __restrict__ x, float* __restrict__ part,
   }
 }
 
+// The same partial sums for V = 1 / 2 / 4 from 16-byte loads: a float4 of the (entry, variable) stream holds lane k of
+// variable k % V, so every lane keeps its own accumulator pair and the four are folded at the end.  Four independent loads per
+// thread and iteration (the scalar form above had 8 bytes per thread in flight and ran at 2.3 TB/s).
+template <int V>
+__global__ void __launch_bounds__(ST_THREADS)
+lift_stats_partial_vec_kernel(const float* __restrict__ x, float* __restrict__ part, long entries) {
+  static_assert(V == 1 || V == 2 || V == 4, "a float4 must hold whole entries");
+  const int b = blockIdx.y;
+  const float* __restrict__ xb = x + (size_t)b * entries * V;
+  float K[4], s1[4], s2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    K[k] = __ldg(xb + (k % V));
+    s1[k] = 0.f;
+    s2[k] = 0.f;
+  }
+  const long total4 = entries * V / 4;             // entries * V % 4 == 0 (checked by the caller)
+  const long per = (total4 + gridDim.x - 1) / gridDim.x;
+  const long i0 = (long)blockIdx.x * per;
+  long i1 = i0 + per;
+  if (i1 > total4) i1 = total4;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(xb);
+  auto add = [&](const float4& q) {
+    const float d0 = q.x - K[0], d1 = q.y - K[1], d2 = q.z - K[2], d3 = q.w - K[3];
+    s1[0] += d0; s2[0] = fmaf(d0, d0, s2[0]);
+    s1[1] += d1; s2[1] = fmaf(d1, d1, s2[1]);
+    s1[2] += d2; s2[2] = fmaf(d2, d2, s2[2]);
+    s1[3] += d3; s2[3] = fmaf(d3, d3, s2[3]);
+  };
+  long i = i0 + threadIdx.x;
+  for (; i + 3 * ST_THREADS < i1; i += 4 * ST_THREADS) {
+    const float4 q0 = __ldg(x4 + i), q1 = __ldg(x4 + i + ST_THREADS), q2 = __ldg(x4 + i + 2 * ST_THREADS),
+                 q3 = __ldg(x4 + i + 3 * ST_THREADS);
+    add(q0); add(q1); add(q2); add(q3);
+  }
+  for (; i < i1; i += ST_THREADS) add(__ldg(x4 + i));
+  // fold the lanes of one variable: lane k belongs to variable k % V
+  float a[V], c[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) { a[v] = 0.f; c[v] = 0.f; }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { a[k % V] += s1[k]; c[k % V] += s2[k]; }
+  __shared__ float red[ST_THREADS / 32][V][2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    float av = a[v], cv = c[v];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      av += __shfl_xor_sync(0xffffffffu, av, off);
+      cv += __shfl_xor_sync(0xffffffffu, cv, off);
+    }
+    if (lane == 0) { red[warp][v][0] = av; red[warp][v][1] = cv; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * V) {
+    const int v = threadIdx.x >> 1, k = threadIdx.x & 1;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_THREADS / 32; ++w) s += red[w][v][k];
+    part[(((size_t)b * gridDim.x + blockIdx.x) * V + v) * 2 + k] = s;
+  }
+}
+
 // stats[b][0][v] = mean, stats[b][1][v] = std + 1e-7   (torch.std_mean: unbiased)
 __global__ void lift_stats_final_kernel(const float* __restrict__ x, const float* __restrict__ part,
                                         float* __restrict__ stats, long entries, int V, int B, int nblk) {
@@ -972,7 +1036,12 @@ extern "C" int fno_lift_stats(const float* x, float* stats, void* work, int B, l
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* part = static_cast<float*>(work);
-  lift_stats_partial_kernel<<<dim3(ST_BLOCKS, B), ST_THREADS, 0, st>>>(x, part, entries, V);
+  // 16-byte loads when a float4 holds whole entries and every sample starts 16-byte aligned
+  const bool vec = (V == 1 || V == 2 || V == 4) && (entries * V) % 4 == 0 && (reinterpret_cast<size_t>(x) & 15u) == 0;
+  if (vec && V == 1) lift_stats_partial_vec_kernel<1><<<dim3(ST_BLOCKS, B), ST_THREADS, 0, st>>>(x, part, entries);
+  else if (vec && V == 2) lift_stats_partial_vec_kernel<2><<<dim3(ST_BLOCKS, B), ST_THREADS, 0, st>>>(x, part, entries);
+  else if (vec && V == 4) lift_stats_partial_vec_kernel<4><<<dim3(ST_BLOCKS, B), ST_THREADS, 0, st>>>(x, part, entries);
+  else lift_stats_partial_kernel<<<dim3(ST_BLOCKS, B), ST_THREADS, 0, st>>>(x, part, entries, V);
   count_launch();
   int rc = check_launch("lift_stats_partial_kernel");
   if (rc != FNO_OK) return rc;
