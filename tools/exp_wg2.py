@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Bypass weight-gradient forms (FNO_WG2 = 0 / 1 / 2, csrc/pointwise.cu) at the cfg-1 layer geometry: parity against an fp64
-einsum on a small ragged case and on the bench geometry, then event-timed launches with L2 flushed in between."""
+"""Bypass weight gradient (csrc/pointwise.cu, wgrad2_partial_kernel) at the cfg-1 layer geometry: parity against an fp64 einsum on
+ragged cases (with and without the fused data gradient), then event-timed launches with L2 flushed in between.  The operand
+feed is chosen once per process: FNO_WG2=0 python tools/exp_wg2.py times the bulk-copy form, the default the tensor-map form
+(profiles/r2g_wgrad_forms.md has the sweep over ring shapes that led there)."""
 import os
 import sys
 from pathlib import Path
